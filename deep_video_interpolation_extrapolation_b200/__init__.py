@@ -1,0 +1,15 @@
+"""B200-native optical-flow backward warp + mask-weighted blend.
+
+A drop-in for ONE hot path of lzhangbj/deep_video_interpolation_extrapolation
+(utils/net_utils.py:89-129, nets/OpticalUnet.py:123-146): hand-written sm_100a kernels behind a
+C-ABI (include/flowwarp_b200.h), exposed as a PyTorch autograd op.  No CPU / torch fallback.
+"""
+from .net_utils import (FlowWrapper, bidirectional_warp, blend_with_noise, warp, warp_back, warp_blend,
+                        warp_multi)
+from .ops import flow_warp_blend, sample_indices
+
+__all__ = [
+    "FlowWrapper", "warp", "warp_back", "warp_multi", "warp_blend", "bidirectional_warp", "blend_with_noise",
+    "flow_warp_blend", "sample_indices",
+]
+__version__ = "1.0.0"

@@ -1,0 +1,502 @@
+// flowwarp_b200.cu — sm_100a kernels + C-ABI of the flow-warp / blend hot path.
+//
+// Reference semantics: utils/net_utils.py:89-129 and nets/OpticalUnet.py:7-15,123-146 of
+// lzhangbj/deep_video_interpolation_extrapolation (see include/flowwarp_b200.h for the map).
+// HBM-bound gather/scatter: no tensor cores.  One thread per output pixel so that a warp's 32
+// taps of one plane are (nearly) one 128 B line; all channels of all groups are looped inside the
+// thread so the coordinate math, weights and validity are computed once per pixel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/flowwarp_b200.h"
+#include "fwb_coords.cuh"
+
+namespace fwb {
+
+struct GradP {
+  const float* grad_out[FWB_MAX_GROUPS];
+  long long go_sn[FWB_MAX_GROUPS], go_st[FWB_MAX_GROUPS];
+  int go_sc[FWB_MAX_GROUPS], go_sh[FWB_MAX_GROUPS];
+  float* grad_src[FWB_MAX_GROUPS][2];
+  long long gs_sn[FWB_MAX_GROUPS][2], gs_st[FWB_MAX_GROUPS][2];
+  int gs_sc[FWB_MAX_GROUPS][2], gs_sh[FWB_MAX_GROUPS][2];
+  float* grad_flow[2];
+  long long gf_sn[2], gf_sc[2], gf_st[2], gf_sh[2];
+  float* grad_gate[2];
+  long long gg_sn[2], gg_st[2], gg_sh[2];
+  float* grad_blend[2];
+  long long gb_sn[2], gb_st[2], gb_sh[2];
+};
+
+struct Params {
+  Geo geo;
+  DirP dir[2];
+  GroupP grp[FWB_MAX_GROUPS];
+};
+
+constexpr int BX = 64;  // pixels of one row per CTA (2 warps wide)
+constexpr int BY = 4;   // rows per CTA
+
+__device__ __forceinline__ float ldg_if(const float* p, bool ok) { return ok ? __ldg(p) : 0.0f; }
+
+// 4-tap bilinear value; accumulation order nw, ne, sw, se (torch:_decomp/decompositions.py:4515-4537)
+__device__ __forceinline__ float bilinear(const float* __restrict__ s, int o, int sh, unsigned v, float wnw,
+                                          float wne, float wsw, float wse) {
+  const float a = ldg_if(s + o, v & 1u), b = ldg_if(s + o + 1, v & 2u);
+  const float c = ldg_if(s + o + sh, v & 4u), d = ldg_if(s + o + sh + 1, v & 8u);
+  float r = __fmul_rn(a, wnw);
+  r = __fmaf_rn(b, wne, r);
+  r = __fmaf_rn(c, wsw, r);
+  r = __fmaf_rn(d, wse, r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: fused forward warp (+gate) (+blend) for NDIRS directions and all channel groups.
+// ---------------------------------------------------------------------------------------------
+template <int NDIRS>
+__global__ void __launch_bounds__(BX* BY) fwd_kernel(const __grid_constant__ Params P) {
+  const Geo& G = P.geo;
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  if (j >= G.W || i >= G.H) return;
+  const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
+
+  float w[NDIRS][4], bl[NDIRS];
+  int x0[NDIRS], y0[NDIRS];
+  unsigned v[NDIRS];
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    Tap k;
+    compute_tap(G, P.dir[d], n, t, i, j, k);
+    w[d][0] = __fmul_rn(k.ux, k.uy);
+    w[d][1] = __fmul_rn(k.tx, k.uy);
+    w[d][2] = __fmul_rn(k.ux, k.ty);
+    w[d][3] = __fmul_rn(k.tx, k.ty);
+    x0[d] = k.x0;
+    y0[d] = k.y0;
+    v[d] = k.valid;
+    bl[d] = k.blend;
+    has_bl[d] = P.dir[d].blend != nullptr;
+  }
+  for (int g = 0; g < G.n_groups; ++g) {
+    const GroupP& R = P.grp[g];
+    const float* s[NDIRS];
+    int o[NDIRS];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
+      o[d] = y0[d] * R.src_sh[d] + x0[d];
+    }
+    float* out = R.out + n * R.out_sn + t * R.out_st + (long long)i * R.out_sh + j;
+#pragma unroll 4
+    for (int c = 0; c < R.C; ++c) {
+      float r = 0.0f;
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        float a = bilinear(s[d] + (long long)c * R.src_sc[d], o[d], R.src_sh[d], v[d], w[d][0], w[d][1],
+                           w[d][2], w[d][3]);
+        if (has_bl[d]) a = __fmul_rn(a, bl[d]);
+        r = (d == 0) ? a : __fadd_rn(r, a);
+      }
+      __stcs(out + (long long)c * R.out_sc, r);
+    }
+  }
+}
+
+// Debug / parity kernel: integer indices, validity bits, float coordinates of one direction.
+__global__ void indices_kernel(const __grid_constant__ Params P, int d, int* __restrict__ x0,
+                               int* __restrict__ y0, uint8_t* __restrict__ valid, float* __restrict__ ix,
+                               float* __restrict__ iy) {
+  const Geo& G = P.geo;
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  if (j >= G.W || i >= G.H) return;
+  const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
+  Tap k;
+  compute_tap(G, P.dir[d], n, t, i, j, k);
+  const long long o = ((long long)blockIdx.z * G.H + i) * G.W + j;
+  if (x0) x0[o] = k.x0;
+  if (y0) y0[o] = k.y0;
+  if (valid) valid[o] = (uint8_t)k.valid;
+  if (ix) ix[o] = k.ix;
+  if (iy) iy[o] = k.iy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: gradient w.r.t. flow / gate / blend weight — a pure gather, one thread per pixel.
+//   gix = sum_c gw_c * [ uy*(v_ne - v_nw) + ty*(v_se - v_sw) ]
+//   giy = sum_c gw_c * [ ux*(v_sw - v_nw) + tx*(v_se - v_ne) ]       (OOB tap value = 0)
+// which is ATen's grid_sampler_2d_backward accumulation with the common factors pulled out.
+// ---------------------------------------------------------------------------------------------
+template <int NDIRS>
+__global__ void __launch_bounds__(BX* BY) bwd_flow_kernel(const __grid_constant__ Params P,
+                                                          const __grid_constant__ GradP Q) {
+  const Geo& G = P.geo;
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  if (j >= G.W || i >= G.H) return;
+  const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
+
+  Tap k[NDIRS];
+  float gix[NDIRS], giy[NDIRS], gbl[NDIRS];
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    compute_tap(G, P.dir[d], n, t, i, j, k[d]);
+    gix[d] = giy[d] = gbl[d] = 0.0f;
+    has_bl[d] = P.dir[d].blend != nullptr;
+  }
+  for (int g = 0; g < G.n_groups; ++g) {
+    const GroupP& R = P.grp[g];
+    if (!Q.grad_out[g]) continue;
+    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
+    const float* s[NDIRS];
+    int o[NDIRS];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
+      o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
+    }
+#pragma unroll 2
+    for (int c = 0; c < R.C; ++c) {
+      const float gout = __ldcs(go + (long long)c * Q.go_sc[g]);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
+        const int sh = R.src_sh[d];
+        const unsigned v = k[d].valid;
+        const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
+        const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
+        float gw = gout;
+        if (has_bl[d]) {
+          const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
+          gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
+          gw = gout * k[d].blend;
+        }
+        gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
+        giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
+    if (P.dir[d].sign < 0.0f) {
+      gfx = -gfx;
+      gfy = -gfy;
+    }
+    const bool gated = P.dir[d].gate != nullptr;
+    if (Q.grad_gate[d] && gated)
+      Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
+          __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
+    if (Q.grad_flow[d]) {
+      float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
+      o[0] = gated ? gfx * k[d].gate : gfx;
+      o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
+    }
+    if (Q.grad_blend[d] && has_bl[d])
+      Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 3a: gradient w.r.t. the sources by global atomics (the "spill" path; non-deterministic).
+// grad_src must be zero on entry (zero_rows_kernel below).
+// ---------------------------------------------------------------------------------------------
+__global__ void zero_rows_kernel(float* __restrict__ base, long long sn, long long st, int sc, int sh, int N,
+                                 int T, int C, int H, int W) {
+  // blockIdx.x enumerates (n,t,c), blockIdx.y strides over the rows of that plane
+  const int ntc = blockIdx.x;
+  const int c = ntc % C, nt = ntc / C;
+  const int n = nt / T, t = nt - n * T;
+  float* plane = base + n * sn + t * st + (long long)c * sc;
+  for (int i = blockIdx.y; i < H; i += gridDim.y) {
+    float* row = plane + (long long)i * sh;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) row[j] = 0.0f;
+  }
+}
+
+template <int NDIRS>
+__global__ void __launch_bounds__(BX* BY) bwd_src_atomic_kernel(const __grid_constant__ Params P,
+                                                                const __grid_constant__ GradP Q) {
+  const Geo& G = P.geo;
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  if (j >= G.W || i >= G.H) return;
+  const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
+  float w[NDIRS][4], bl[NDIRS];
+  int x0[NDIRS], y0[NDIRS];
+  unsigned v[NDIRS];
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    Tap k;
+    compute_tap(G, P.dir[d], n, t, i, j, k);
+    w[d][0] = __fmul_rn(k.ux, k.uy);
+    w[d][1] = __fmul_rn(k.tx, k.uy);
+    w[d][2] = __fmul_rn(k.ux, k.ty);
+    w[d][3] = __fmul_rn(k.tx, k.ty);
+    x0[d] = k.x0;
+    y0[d] = k.y0;
+    v[d] = k.valid;
+    bl[d] = k.blend;
+    has_bl[d] = P.dir[d].blend != nullptr;
+  }
+  for (int g = 0; g < G.n_groups; ++g) {
+    const GroupP& R = P.grp[g];
+    if (!Q.grad_out[g]) continue;
+    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
+    for (int c = 0; c < R.C; ++c) {
+      const float gout = __ldcs(go + (long long)c * Q.go_sc[g]);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        float* gs = Q.grad_src[g][d];
+        if (!gs) continue;
+        const int sh = Q.gs_sh[g][d];
+        gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d] + (long long)y0[d] * sh + x0[d];
+        const float gw = has_bl[d] ? gout * bl[d] : gout;
+        if (v[d] & 1u) atomicAdd(gs, w[d][0] * gw);
+        if (v[d] & 2u) atomicAdd(gs + 1, w[d][1] * gw);
+        if (v[d] & 4u) atomicAdd(gs + sh, w[d][2] * gw);
+        if (v[d] & 8u) atomicAdd(gs + sh + 1, w[d][3] * gw);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int validate(const fwb_problem* p) {
+  if (!p) return FWB_E_NULL;
+  if (p->N < 0 || p->T < 1 || p->H < 1 || p->W < 1) return FWB_E_SHAPE;
+  if ((long long)p->N * p->T > 65535) return FWB_E_SHAPE;
+  if (p->H > 32767 || p->W > 32767) return FWB_E_RANGE;
+  if (p->n_dirs < 1 || p->n_dirs > 2) return FWB_E_DIRS;
+  if (p->n_groups < 1 || p->n_groups > FWB_MAX_GROUPS) return FWB_E_GROUPS;
+  if (p->padding_mode != FWB_PAD_ZEROS && p->padding_mode != FWB_PAD_BORDER) return FWB_E_MODE;
+  if (p->align_corners != 0 && p->align_corners != 1) return FWB_E_MODE;
+  for (int d = 0; d < p->n_dirs; ++d) {
+    if (!p->dir[d].flow) return FWB_E_NULL;
+    if (p->dir[d].sign != 1.0f && p->dir[d].sign != -1.0f) return FWB_E_MODE;
+    if (((uintptr_t)p->dir[d].flow | (uintptr_t)p->dir[d].gate | (uintptr_t)p->dir[d].blend) & 3u)
+      return FWB_E_ALIGN;
+  }
+  for (int g = 0; g < p->n_groups; ++g) {
+    const fwb_group* R = &p->grp[g];
+    if (R->C < 1) return FWB_E_SHAPE;
+    for (int d = 0; d < p->n_dirs; ++d) {
+      if (!R->src[d]) return FWB_E_NULL;
+      if ((uintptr_t)R->src[d] & 3u) return FWB_E_ALIGN;
+      // in-image offsets are 32-bit in the kernels
+      if ((long long)R->C * R->src_sc[d] + (long long)(p->H + 2) * R->src_sh[d] > 2147483647LL ||
+          R->src_sc[d] < 0 || R->src_sh[d] < 0)
+        return FWB_E_SHAPE;
+    }
+  }
+  return 0;
+}
+
+static void to_params(const fwb_problem* p, Params& P) {
+  Geo& G = P.geo;
+  G.N = p->N;
+  G.T = p->T;
+  G.H = p->H;
+  G.W = p->W;
+  G.n_dirs = p->n_dirs;
+  G.n_groups = p->n_groups;
+  G.pad_border = p->padding_mode == FWB_PAD_BORDER;
+  G.align = p->align_corners;
+  G.stepx = p->W > 1 ? 2.0f / (float)(p->W - 1) : 0.0f;
+  G.stepy = p->H > 1 ? 2.0f / (float)(p->H - 1) : 0.0f;
+  for (int d = 0; d < 2; ++d) {
+    const fwb_dir& s = p->dir[d < p->n_dirs ? d : 0];
+    DirP& D = P.dir[d];
+    D.flow = s.flow;
+    D.flow_sn = s.flow_sn;
+    D.flow_sc = s.flow_sc;
+    D.flow_st = s.flow_st;
+    D.flow_sh = s.flow_sh;
+    D.gate = s.gate;
+    D.gate_sn = s.gate_sn;
+    D.gate_st = s.gate_st;
+    D.gate_sh = s.gate_sh;
+    D.blend = s.blend;
+    D.blend_sn = s.blend_sn;
+    D.blend_st = s.blend_st;
+    D.blend_sh = s.blend_sh;
+    D.sign = s.sign;
+  }
+  for (int g = 0; g < FWB_MAX_GROUPS; ++g) {
+    const fwb_group& s = p->grp[g < p->n_groups ? g : 0];
+    GroupP& R = P.grp[g];
+    R.C = s.C;
+    for (int d = 0; d < 2; ++d) {
+      const int e = d < p->n_dirs ? d : 0;
+      R.src[d] = s.src[e];
+      R.src_sn[d] = s.src_sn[e];
+      R.src_st[d] = s.src_st[e];
+      R.src_sc[d] = (int)s.src_sc[e];
+      R.src_sh[d] = (int)s.src_sh[e];
+    }
+    R.out = s.out;
+    R.out_sn = s.out_sn;
+    R.out_st = s.out_st;
+    R.out_sc = (int)s.out_sc;
+    R.out_sh = (int)s.out_sh;
+  }
+}
+
+static int to_grads(const fwb_problem* p, const fwb_grads* q, GradP& Q) {
+  if (!q) return FWB_E_NULL;
+  for (int g = 0; g < FWB_MAX_GROUPS; ++g) {
+    const bool on = g < p->n_groups;
+    Q.grad_out[g] = on ? q->grad_out[g] : nullptr;
+    Q.go_sn[g] = q->go_sn[g];
+    Q.go_st[g] = q->go_st[g];
+    Q.go_sc[g] = (int)q->go_sc[g];
+    Q.go_sh[g] = (int)q->go_sh[g];
+    if ((uintptr_t)Q.grad_out[g] & 3u) return FWB_E_ALIGN;
+    for (int d = 0; d < 2; ++d) {
+      Q.grad_src[g][d] = (on && d < p->n_dirs) ? q->grad_src[g][d] : nullptr;
+      Q.gs_sn[g][d] = q->gs_sn[g][d];
+      Q.gs_st[g][d] = q->gs_st[g][d];
+      Q.gs_sc[g][d] = (int)q->gs_sc[g][d];
+      Q.gs_sh[g][d] = (int)q->gs_sh[g][d];
+      if ((uintptr_t)Q.grad_src[g][d] & 3u) return FWB_E_ALIGN;
+    }
+  }
+  for (int d = 0; d < 2; ++d) {
+    const bool on = d < p->n_dirs;
+    Q.grad_flow[d] = on ? q->grad_flow[d] : nullptr;
+    Q.gf_sn[d] = q->gf_sn[d];
+    Q.gf_sc[d] = q->gf_sc[d];
+    Q.gf_st[d] = q->gf_st[d];
+    Q.gf_sh[d] = q->gf_sh[d];
+    Q.grad_gate[d] = on ? q->grad_gate[d] : nullptr;
+    Q.gg_sn[d] = q->gg_sn[d];
+    Q.gg_st[d] = q->gg_st[d];
+    Q.gg_sh[d] = q->gg_sh[d];
+    Q.grad_blend[d] = on ? q->grad_blend[d] : nullptr;
+    Q.gb_sn[d] = q->gb_sn[d];
+    Q.gb_st[d] = q->gb_st[d];
+    Q.gb_sh[d] = q->gb_sh[d];
+  }
+  return 0;
+}
+
+static dim3 pixel_grid(const fwb_problem* p) {
+  return dim3((p->W + BX - 1) / BX, (p->H + BY - 1) / BY, p->N * p->T);
+}
+
+}  // namespace fwb
+
+using namespace fwb;
+
+extern "C" {
+
+int32_t fwb_version(void) { return FWB_VERSION; }
+
+const char* fwb_strerror(int32_t code) {
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case 0: return "ok";
+    case FWB_E_NULL: return "a required pointer is NULL";
+    case FWB_E_SHAPE: return "N/T/H/W/C out of range (empty spatial dims are an error)";
+    case FWB_E_DIRS: return "n_dirs must be 1 or 2";
+    case FWB_E_GROUPS: return "n_groups must be in 1..FWB_MAX_GROUPS";
+    case FWB_E_MODE: return "unknown padding_mode / align_corners / sign";
+    case FWB_E_ALIGN: return "pointer not 4-byte aligned";
+    case FWB_E_WORKSPACE: return "workspace missing or too small";
+    case FWB_E_RANGE: return "H or W above 32767";
+    default: return "unknown error";
+  }
+}
+
+int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  for (int g = 0; g < p->n_groups; ++g) {
+    if (!p->grp[g].out) return FWB_E_NULL;
+    if ((uintptr_t)p->grp[g].out & 3u) return FWB_E_ALIGN;
+  }
+  if (p->N == 0) return 0;
+  Params P;
+  to_params(p, P);
+  cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid = pixel_grid(p), block(BX, BY);
+  if (p->n_dirs == 2)
+    fwd_kernel<2><<<grid, block, 0, s>>>(P);
+  else
+    fwd_kernel<1><<<grid, block, 0, s>>>(P);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0, uint8_t* valid,
+                           float* ix, float* iy, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if (d < 0 || d >= p->n_dirs) return FWB_E_DIRS;
+  if (p->N == 0) return 0;
+  Params P;
+  to_params(p, P);
+  indices_kernel<<<pixel_grid(p), dim3(BX, BY), 0, (cudaStream_t)stream>>>(P, d, x0, y0, valid, ix, iy);
+  return (int32_t)cudaGetLastError();
+}
+
+size_t fwb_workspace_bytes(const fwb_problem* p) {
+  if (validate(p)) return 0;
+  return 0;
+}
+
+int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  int rc = validate(p);
+  if (rc) return rc;
+  Params P;
+  GradP Q;
+  to_params(p, P);
+  rc = to_grads(p, g, Q);
+  if (rc) return rc;
+  if (p->N == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid = pixel_grid(p), block(BX, BY);
+  if (p->n_dirs == 2)
+    bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
+  else
+    bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  int rc = validate(p);
+  if (rc) return rc;
+  Params P;
+  GradP Q;
+  to_params(p, P);
+  rc = to_grads(p, g, Q);
+  if (rc) return rc;
+  if (p->N == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int gi = 0; gi < p->n_groups; ++gi)
+    for (int d = 0; d < p->n_dirs; ++d) {
+      float* gs = Q.grad_src[gi][d];
+      if (!gs) continue;
+      const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
+      const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
+      zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d],
+                                          p->N, Tn, p->grp[gi].C, p->H, p->W);
+    }
+  const dim3 grid = pixel_grid(p), block(BX, BY);
+  if (p->n_dirs == 2)
+    bwd_src_atomic_kernel<2><<<grid, block, 0, s>>>(P, Q);
+  else
+    bwd_src_atomic_kernel<1><<<grid, block, 0, s>>>(P, Q);
+  return (int32_t)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+"""PyTorch custom op over the C-ABI: fused flow warp (+gate) (+blend), forward and backward.
+
+`flow_warp_blend` is the one op every reference call site maps onto:
+
+    FlowWrapper.forward   utils/net_utils.py:93-114     1 direction, sign -1, zeros padding
+    warp / warp_back      utils/net_utils.py:116-129    + gate mask, T frames in one launch
+    OpticalUnet warps     nets/OpticalUnet.py:123-146   2 directions, border padding, blend masks
+
+torch is used for device memory, streams and autograd plumbing only; all arithmetic runs in
+libflowwarp_b200.so.  There is no CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib as L
+from ._problem import fill_grads, fill_problem
+
+Tensor = torch.Tensor
+
+
+@dataclass(frozen=True)
+class _Cfg:
+    n_dirs: int
+    n_groups: int
+    signs: Tuple[float, ...]
+    padding_mode: int
+    align_corners: bool
+    deterministic: bool
+    N: int
+    T: int
+    H: int
+    W: int
+
+
+def _ptr(x: Tensor) -> int:
+    return x.data_ptr()
+
+
+def _strides(x: Tensor):
+    return x.stride()
+
+
+def _wcontig(x: Optional[Tensor]) -> Optional[Tensor]:
+    if x is None:
+        return None
+    if x.stride(-1) != 1 and x.size(-1) != 1:
+        return x.contiguous()
+    if x.size(-1) == 1 and x.stride(-1) != 1:
+        return x.contiguous()
+    return x
+
+
+def _expand_t(s: Tensor, T: int) -> Tensor:
+    """[N,1,C,H,W] -> stride-0 view [N,T,C,H,W] (one source frame feeds all T flows, utils/net_utils.py:118)."""
+    return s.expand(s.shape[0], T, *s.shape[2:]) if s.shape[1] != T else s
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _WarpBlendFn(torch.autograd.Function):
+    """tensors = flows[D] + gates[D] + blends[D] + srcs[G*D] (g-major); all already canonical 5-D/4-D."""
+
+    @staticmethod
+    def forward(ctx, cfg: _Cfg, *tensors):
+        D, G = cfg.n_dirs, cfg.n_groups
+        tensors = tuple(_wcontig(t) for t in tensors)
+        flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        srcs = [[_expand_t(s, cfg.T) for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
+        dev = flows[0].device
+        outs = [torch.empty((cfg.N, cfg.T, srcs[g][0].shape[2], cfg.H, cfg.W), dtype=torch.float32, device=dev)
+                for g in range(G)]
+        lib = L.load()
+        with torch.cuda.device(dev):
+            p = fill_problem(N=cfg.N, T=cfg.T, H=cfg.H, W=cfg.W, flows=flows, gates=gates, blends=blends,
+                             signs=cfg.signs, srcs=srcs, outs=outs, padding_mode=cfg.padding_mode,
+                             align_corners=cfg.align_corners,
+                             flags=L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0,
+                             ptr=_ptr, strides=_strides)
+            L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), _stream_ptr(dev)), "fwb_warp_blend_forward")
+        ctx.cfg = cfg
+        ctx.save_for_backward(*[t for t in tensors if t is not None])
+        ctx.present = [t is not None for t in tensors]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        cfg: _Cfg = ctx.cfg
+        D, G = cfg.n_dirs, cfg.n_groups
+        it = iter(ctx.saved_tensors)
+        tensors = [next(it) if pr else None for pr in ctx.present]
+        flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        srcs = [[_expand_t(s, cfg.T) for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
+        need = ctx.needs_input_grad[1:]
+        dev = flows[0].device
+        N, T, H, W = cfg.N, cfg.T, cfg.H, cfg.W
+
+        gos = [None if g is None else _wcontig(g) for g in grad_outs]
+        if all(g is None for g in gos):
+            return (None,) + (None,) * len(tensors)
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_flows = [torch.empty((N, 2, T, H, W), **f32) if need[d] else None for d in range(D)]
+        g_gates = [torch.empty((N, T, H, W), **f32) if (need[D + d] and gates[d] is not None) else None
+                   for d in range(D)]
+        g_blends = [torch.empty((N, T, H, W), **f32) if (need[2 * D + d] and blends[d] is not None) else None
+                    for d in range(D)]
+        g_srcs: List[List[Optional[Tensor]]] = []
+        for g in range(G):
+            row = []
+            for d in range(D):
+                s = srcs[g][d]
+                if need[3 * D + g * D + d] and gos[g] is not None:
+                    shared = s.stride(1) == 0 and T > 1
+                    buf = torch.empty((N, 1 if shared else T, s.shape[2], H, W), **f32)
+                    row.append(buf.expand(N, T, s.shape[2], H, W) if shared else buf)
+                else:
+                    row.append(None)
+            g_srcs.append(row)
+
+        lib = L.load()
+        with torch.cuda.device(dev):
+            p = fill_problem(N=N, T=T, H=H, W=W, flows=flows, gates=gates, blends=blends, signs=cfg.signs,
+                             srcs=srcs, outs=None, padding_mode=cfg.padding_mode,
+                             align_corners=cfg.align_corners,
+                             flags=L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0,
+                             ptr=_ptr, strides=_strides)
+            q = fill_grads(p, grad_outs=gos, grad_srcs=g_srcs, grad_flows=g_flows, grad_gates=g_gates,
+                           grad_blends=g_blends, ptr=_ptr, strides=_strides)
+            nbytes = int(lib.fwb_workspace_bytes(ctypes.byref(p)))
+            ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+            st = _stream_ptr(dev)
+            want_src = any(x is not None for row in g_srcs for x in row)
+            want_flow = any(x is not None for x in g_flows + g_gates + g_blends)
+            # kernel 2 also fills the segment tables kernel 3 consumes -> always first
+            if want_flow or want_src:
+                L.check(lib.fwb_warp_blend_backward_flow(ctypes.byref(p), ctypes.byref(q), ws.data_ptr(), nbytes, st),
+                        "fwb_warp_blend_backward_flow")
+            if want_src:
+                L.check(lib.fwb_warp_blend_backward_src(ctypes.byref(p), ctypes.byref(q), ws.data_ptr(), nbytes, st),
+                        "fwb_warp_blend_backward_src")
+        flat_src = []
+        for g in range(G):
+            for d in range(D):
+                x = g_srcs[g][d]
+                if x is not None and x.stride(1) == 0 and T > 1:
+                    x = x[:, :1]  # the kernel already summed over the T frames that share this source
+                flat_src.append(x)
+        return (None, *g_flows, *g_gates, *g_blends, *flat_src)
+
+
+def _as_list(x, n, what):
+    if x is None:
+        return [None] * n
+    if isinstance(x, Tensor):
+        x = [x]
+    x = list(x)
+    if len(x) != n:
+        raise ValueError(f"{what}: expected {n} entries, got {len(x)}")
+    return x
+
+
+def _canon_mask(m: Optional[Tensor], N, T, H, W, what) -> Optional[Tensor]:
+    if m is None:
+        return None
+    if m.dim() == 3:  # [N,H,W]
+        m = m.unsqueeze(1)
+    if m.dim() == 5 and m.shape[2] == 1:  # [N,T,1,H,W]
+        m = m.squeeze(2)
+    if m.dim() != 4:
+        raise ValueError(f"{what}: expected [N,T,H,W] / [N,1,H,W] / [N,H,W], got {tuple(m.shape)}")
+    if m.shape[0] != N or m.shape[2] != H or m.shape[3] != W or m.shape[1] not in (1, T):
+        raise ValueError(f"{what}: shape {tuple(m.shape)} does not match N={N} T={T} H={H} W={W}")
+    if m.shape[1] != T:
+        m = m.expand(N, T, H, W)
+    return m
+
+
+def flow_warp_blend(
+    srcs: Sequence[Union[Tensor, Sequence[Tensor]]],
+    flows: Union[Tensor, Sequence[Tensor]],
+    gates: Union[None, Tensor, Sequence[Optional[Tensor]]] = None,
+    blends: Union[None, Tensor, Sequence[Optional[Tensor]]] = None,
+    signs: Union[None, float, Sequence[float]] = None,
+    padding_mode: str = "zeros",
+    align_corners: bool = False,
+    deterministic: bool = False,
+) -> List[Tensor]:
+    """out[g] = sum_d blend_d * grid_sample(srcs[g][d], base + sign_d * flow_d * gate_d).
+
+    srcs    one entry per channel group (e.g. RGB, seg) sharing the flows/masks; each entry is a
+            tensor (1 direction) or a sequence with one tensor per direction; [N,C,H,W] or [N,T,C,H,W]
+    flows   one per direction; [N,2,H,W] or [N,2,T,H,W]; normalised units, channel 0 horizontal
+    gates   per direction or None; flow-gating mask (utils/net_utils.py:118)
+    blends  per direction or None; blend weight of that direction's warp (nets/OpticalUnet.py:141-146)
+    signs   per direction, -1 (`base - flow`, default) or +1 (`base + flow`)
+    Returns one [N,C,H,W] (all inputs 4-D) or [N,T,C,H,W] tensor per group.
+    """
+    if isinstance(flows, Tensor):
+        flows = [flows]
+    flows = list(flows)
+    D = len(flows)
+    if D not in (1, 2):
+        raise ValueError(f"flow_warp_blend: 1 or 2 directions supported, got {D}")
+    if isinstance(srcs, Tensor):
+        srcs = [srcs]
+    groups = [[s] if isinstance(s, Tensor) else list(s) for s in srcs]
+    G = len(groups)
+    if not 1 <= G <= L.FWB_MAX_GROUPS:
+        raise ValueError(f"flow_warp_blend: 1..{L.FWB_MAX_GROUPS} channel groups supported, got {G}")
+    gates, blends = _as_list(gates, D, "gates"), _as_list(blends, D, "blends")
+    if signs is None:
+        signs = [-1.0] * D
+    elif isinstance(signs, (int, float)):
+        signs = [float(signs)] * D
+    signs = tuple(float(s) for s in signs)
+    if len(signs) != D or any(s not in (-1.0, 1.0) for s in signs):
+        raise ValueError("signs: one of -1/+1 per direction")
+    if padding_mode not in ("zeros", "border"):
+        raise ValueError(f"padding_mode must be 'zeros' or 'border', got {padding_mode!r}")
+
+    f0 = flows[0]
+    every = [t for t in flows + gates + blends + [s for g in groups for s in g] if t is not None]
+    for t in every:
+        if not isinstance(t, Tensor):
+            raise TypeError("flow_warp_blend: tensors expected")
+        if not t.is_cuda:
+            raise RuntimeError("flow_warp_blend: CUDA tensors required (this library has no CPU path)")
+        if t.device != f0.device:
+            raise RuntimeError(f"flow_warp_blend: all tensors must be on {f0.device}, got {t.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"flow_warp_blend: float32 required, got {t.dtype}")
+
+    five_d = any(f.dim() == 5 for f in flows) or any(s.dim() == 5 for g in groups for s in g)
+    cflows = []
+    for f in flows:
+        if f.dim() == 4:
+            f = f.unsqueeze(2)
+        if f.dim() != 5 or f.shape[1] != 2:
+            raise RuntimeError(f"flow must be [N,2,H,W] or [N,2,T,H,W], got {tuple(f.shape)}")
+        cflows.append(f)
+    N, _, T, H, W = cflows[0].shape
+    if H < 1 or W < 1:
+        raise RuntimeError(f"flow_warp_blend: non-empty spatial dims required, got H={H} W={W}")
+    for f in cflows:
+        if tuple(f.shape) != (N, 2, T, H, W):
+            raise RuntimeError("flow_warp_blend: all flows must share one shape")
+    cgates = [_canon_mask(m, N, T, H, W, "gate") for m in gates]
+    cblends = [_canon_mask(m, N, T, H, W, "blend") for m in blends]
+    csrcs = []
+    for g in groups:
+        if len(g) != D:
+            raise ValueError(f"each source group needs {D} tensors (one per direction), got {len(g)}")
+        row = []
+        for s in g:
+            if s.dim() == 4:
+                s = s.unsqueeze(1)
+            if s.dim() != 5:
+                raise RuntimeError(f"source must be [N,C,H,W] or [N,T,C,H,W], got {tuple(s.shape)}")
+            if s.shape[0] != N or s.shape[3] != H or s.shape[4] != W:
+                raise RuntimeError(
+                    f"source {tuple(s.shape)} and flow {tuple(cflows[0].shape)} disagree on batch or spatial size")
+            if s.shape[1] not in (1, T):
+                raise RuntimeError(f"source has {s.shape[1]} frames, flow has {T}")
+            if s.shape[2] < 1:
+                raise RuntimeError("source needs at least one channel")
+            row.append(s)  # a single frame stays [N,1,C,H,W]; the Function expands it (T-stride 0)
+        if any(s.shape[2] != row[0].shape[2] for s in row):
+            raise RuntimeError("both directions of a group must have the same channel count")
+        csrcs.append(row)
+
+    cfg = _Cfg(D, G, signs, L.FWB_PAD_BORDER if padding_mode == "border" else L.FWB_PAD_ZEROS,
+               bool(align_corners), bool(deterministic), N, T, H, W)
+    flat = [*cflows, *cgates, *cblends, *[s for row in csrcs for s in row]]
+    outs = list(_WarpBlendFn.apply(cfg, *flat))
+    if not five_d:
+        outs = [o.squeeze(1) for o in outs]
+    return outs
+
+
+def sample_indices(flow: Tensor, gate: Optional[Tensor] = None, sign: float = -1.0,
+                   padding_mode: str = "zeros", align_corners: bool = False):
+    """Debug / parity: (x0, y0, valid_bits, ix, iy) the kernels use for `flow` [N,2,H,W] or [N,2,T,H,W].
+
+    x0,y0 int32, valid uint8 (bit0 nw, bit1 ne, bit2 sw, bit3 se), ix,iy float32; shape [N,T,H,W].
+    """
+    if not flow.is_cuda:
+        raise RuntimeError("sample_indices: CUDA tensors required")
+    f = flow.unsqueeze(2) if flow.dim() == 4 else flow
+    f = _wcontig(f)
+    N, _, T, H, W = f.shape
+    g = _wcontig(_canon_mask(gate, N, T, H, W, "gate"))
+    dev = f.device
+    dummy = torch.empty((N, 1, 1, H, W), dtype=torch.float32, device=dev).expand(N, T, 1, H, W)
+    x0 = torch.empty((N, T, H, W), dtype=torch.int32, device=dev)
+    y0 = torch.empty_like(x0)
+    valid = torch.empty((N, T, H, W), dtype=torch.uint8, device=dev)
+    ix = torch.empty((N, T, H, W), dtype=torch.float32, device=dev)
+    iy = torch.empty_like(ix)
+    lib = L.load()
+    with torch.cuda.device(dev):
+        p = fill_problem(N=N, T=T, H=H, W=W, flows=[f], gates=[g], blends=[None], signs=[sign], srcs=[[dummy]],
+                         outs=None, padding_mode=L.FWB_PAD_BORDER if padding_mode == "border" else L.FWB_PAD_ZEROS,
+                         align_corners=align_corners, flags=0, ptr=_ptr, strides=_strides)
+        L.check(lib.fwb_sample_indices(ctypes.byref(p), 0, x0.data_ptr(), y0.data_ptr(), valid.data_ptr(),
+                                       ix.data_ptr(), iy.data_ptr(), _stream_ptr(dev)), "fwb_sample_indices")
+    return x0, y0, valid, ix, iy

@@ -1,0 +1,152 @@
+/*
+ * flowwarp_b200.h — C-ABI of the B200-native optical-flow backward warp + mask-weighted blend.
+ *
+ * This is the drop-in boundary for ONE hot path of lzhangbj/deep_video_interpolation_extrapolation:
+ *
+ *   reference interface replaced                                   file:line (under /root/reference)
+ *   ------------------------------------------------------------   ---------------------------------
+ *   FlowWrapper.forward(x, flow)   base grid - flow, grid_sample    utils/net_utils.py:93-114
+ *   warp(frame, flow, opt, floww, mask)       T frames, gated flow  utils/net_utils.py:116-121
+ *   warp_back(frame, flowback, opt, floww, mask)                    utils/net_utils.py:124-129
+ *   inline bidirectional warp (border padding)                      nets/OpticalUnet.py:7-15,123-139
+ *   mask weighting of the two warps                                 nets/OpticalUnet.py:141-146
+ *   autograd of all of the above (ATen grid_sampler_2d_backward)    torch: ATen/native/GridSampler.h:43-83
+ *
+ * The reference is pure Python over torch; it has no FFI of its own.  The binding a maintainer
+ * adds is the ctypes stub in deep_video_interpolation_extrapolation_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers + sizes + strides; no torch types.  All tensors are fp32.  Strides are in ELEMENTS.
+ *     The innermost (W) stride of every tensor is 1.
+ *   - logical batch is (N, T): T = opt.vid_length frames that share one launch.  A tensor that is
+ *     shared by all T frames (the single source frame of warp()) passes a T-stride of 0.
+ *   - every function launches asynchronously on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, keeps no global mutable state, never throws and never aborts.
+ *   - return value: 0 = ok; > 0 = a cudaError_t from a launch; < 0 = FWB_E_* argument error.
+ *   - sampling arithmetic (bit-exact contract, see DESIGN.md "Coordinate arithmetic"):
+ *        bx[j]   = linspace(-1,1,W)[j]  (CPU torch.linspace bit pattern; -1 when W == 1)
+ *        f       = gate ? flow*gate : flow                  (one fp32 rounding)
+ *        gx      = sign < 0 ? bx - f : bx + f
+ *        ix      = align_corners ? ((gx+1)/2)*(W-1) : fma(gx+1, W, -1)/2
+ *        border  : ix = min(W-1, max(ix, 0));  non-finite or out-of-int-range -> -100
+ *        x0      = floor(ix); taps (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1); valid bit per tap = in image
+ *        out[c]  = sum_d  blend_d * ( v_nw*nw + v_ne*ne + v_sw*sw + v_se*se )   in that order
+ */
+#ifndef FLOWWARP_B200_H
+#define FLOWWARP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FWB_VERSION 0x00010000 /* major.minor.patch = 1.0.0 */
+#define FWB_MAX_GROUPS 4       /* channel groups that share flow/mask (RGB, seg, ...) */
+
+/* padding_mode — torch F.grid_sample padding_mode (utils/net_utils.py:113 uses zeros,
+ * nets/OpticalUnet.py:135,139 uses border) */
+#define FWB_PAD_ZEROS 0
+#define FWB_PAD_BORDER 1
+
+/* flags */
+#define FWB_FLAG_DETERMINISTIC 1u /* grad_src: owner-gather kernel only, bit-exact run to run */
+
+/* argument errors (negative return values) */
+#define FWB_E_NULL -1      /* a required pointer is NULL */
+#define FWB_E_SHAPE -2     /* N,T,H,W,C out of range (empty spatial dims are an error, as in torch) */
+#define FWB_E_DIRS -3      /* n_dirs not in {1,2} */
+#define FWB_E_GROUPS -4    /* n_groups not in 1..FWB_MAX_GROUPS */
+#define FWB_E_MODE -5      /* unknown padding_mode / align_corners / sign */
+#define FWB_E_ALIGN -6     /* a pointer is not 4-byte aligned */
+#define FWB_E_WORKSPACE -7 /* workspace missing or too small */
+#define FWB_E_RANGE -8     /* H or W above 32767 (segment tables are int16) */
+
+/* One warp direction: its flow, optional flow-gating mask (utils/net_utils.py:118 `flow*mask`)
+ * and optional blend weight (nets/OpticalUnet.py:141-146). */
+typedef struct fwb_dir {
+  const float* flow; /* [N,2,T,H,W]: channel 0 horizontal, 1 vertical, normalised units */
+  int64_t flow_sn, flow_sc, flow_st, flow_sh;
+  const float* gate; /* optional [N,T,H,W] */
+  int64_t gate_sn, gate_st, gate_sh;
+  const float* blend; /* optional [N,T,H,W] */
+  int64_t blend_sn, blend_st, blend_sh;
+  float sign; /* -1: grid = base - flow (warp, forward flow); +1: grid = base + flow (warp_back) */
+  int32_t _pad;
+} fwb_dir;
+
+/* One channel group: per-direction source planes and the output planes. */
+typedef struct fwb_group {
+  int32_t C;
+  int32_t _pad;
+  const float* src[2]; /* [N,T,C,H,W] (T-stride 0 when one frame feeds all T) */
+  int64_t src_sn[2], src_st[2], src_sc[2], src_sh[2];
+  float* out; /* [N,T,C,H,W] */
+  int64_t out_sn, out_st, out_sc, out_sh;
+} fwb_group;
+
+typedef struct fwb_problem {
+  int32_t N, T, H, W;
+  int32_t n_dirs;   /* 1 or 2 */
+  int32_t n_groups; /* 1..FWB_MAX_GROUPS */
+  int32_t padding_mode;
+  int32_t align_corners;
+  uint32_t flags;
+  int32_t _pad;
+  fwb_dir dir[2];
+  fwb_group grp[FWB_MAX_GROUPS];
+} fwb_problem;
+
+/* Gradient buffers for the backward entry points.  Any output pointer may be NULL (= not needed). */
+typedef struct fwb_grads {
+  const float* grad_out[FWB_MAX_GROUPS]; /* [N,T,C,H,W], strides below */
+  int64_t go_sn[FWB_MAX_GROUPS], go_st[FWB_MAX_GROUPS], go_sc[FWB_MAX_GROUPS], go_sh[FWB_MAX_GROUPS];
+  float* grad_src[FWB_MAX_GROUPS][2]; /* same logical shape as src; T-stride 0 => summed over T */
+  int64_t gs_sn[FWB_MAX_GROUPS][2], gs_st[FWB_MAX_GROUPS][2], gs_sc[FWB_MAX_GROUPS][2],
+      gs_sh[FWB_MAX_GROUPS][2];
+  float* grad_flow[2]; /* [N,2,T,H,W] */
+  int64_t gf_sn[2], gf_sc[2], gf_st[2], gf_sh[2];
+  float* grad_gate[2]; /* [N,T,H,W] */
+  int64_t gg_sn[2], gg_st[2], gg_sh[2];
+  float* grad_blend[2]; /* [N,T,H,W] */
+  int64_t gb_sn[2], gb_st[2], gb_sh[2];
+} fwb_grads;
+
+/* Library version (FWB_VERSION of the build). */
+int32_t fwb_version(void);
+
+/* Human-readable text for a return code of this library (static storage). */
+const char* fwb_strerror(int32_t code);
+
+/* Kernel 1 — fused forward: flow->coordinate, floor/fraction, validity, 4-tap bilinear gather
+ * over every channel of every group, for 1 or 2 directions, and the blend-weighted sum.
+ * Replaces utils/net_utils.py:93-121 (+124-129) and nets/OpticalUnet.py:123-146. */
+int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream);
+
+/* Debug / parity: integer sample indices and validity bits of direction `d`.
+ * x0,y0: int32 [N,T,H,W] contiguous; valid: uint8 [N,T,H,W], bit0 nw, bit1 ne, bit2 sw, bit3 se.
+ * Same device function as the forward kernel. */
+int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0,
+                           uint8_t* valid, float* ix, float* iy, void* stream);
+
+/* Bytes of scratch the backward entry points need for this problem (segment tables of the
+ * owner-gather kernel); 0 is a valid answer. */
+size_t fwb_workspace_bytes(const fwb_problem* p);
+
+/* Kernel 2 — gradient w.r.t. flow, gate and blend weight, as a gather (no atomics).
+ * Replaces autograd of grid_sample's grid input + the mul/sub/transposes around it
+ * (utils/net_utils.py:109-113,118).  Also fills the per-segment tap bounding boxes in
+ * `workspace` that kernel 3 consumes (so call it before fwb_warp_blend_backward_src). */
+int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* Kernel 3 — gradient w.r.t. the sources (image / segmentation planes).
+ * Replaces the atomicAdd scatter of ATen grid_sampler_2d_backward. */
+int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWWARP_B200_H */
