@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — warp+blend forward+backward throughput (Gpix/s) and HBM-roofline fraction on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of synthetic Cityscapes-shaped clips: the fused
+bidirectional warp + mask-weighted blend forward (kernel 1), the flow/mask gradient (kernel 2) and the
+source-gradient (kernel 3), C = 3 RGB + 20 seg channels, per-GPU batch fixed (weak scaling, batch-sharded,
+no collective in the op).  Default workload = BASELINE.json configs[1]: 256x512, batch 16, 1xB200.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (N per GPU, H, W, sigma_px, chained steps, allreduce params)
+    2: dict(name="config2: InterNet warp+blend fwd+bwd 256x512 batch 16", N=16, H=256, W=512, sigma=8.0, chain=1, allreduce=0),
+    3: dict(name="config3: ExtraNet 3-step chained warp 512x1024 batch 8", N=8, H=512, W=1024, sigma=8.0, chain=3, allreduce=0),
+    4: dict(name="config4: int_9 full-res 1024x2048 batch 4 per GPU", N=4, H=1024, W=2048, sigma=32.0, chain=1, allreduce=0),
+    5: dict(name="config5: InterGAN/refine step 256x512 batch 8 per GPU + NCCL grad all-reduce", N=8, H=256, W=512, sigma=8.0, chain=1,
+            allreduce=3_821_891),
+}
+CH = (3, 20)  # RGB + 20-class seg
+C_TOTAL = sum(CH)
+BYTES_PER_PIX = 32 * C_TOTAL + 72  # bidirectional warp+blend fwd+bwd, fp32
+# per-kernel algorithmic bytes/pixel when the three kernels run as separate launches
+KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48, "backward_src": 12 * C_TOTAL + 24}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------- inputs
+def make_inputs(cfg, device, seed=0):
+    """Seeded synthetic clip batch generated with torch on `device`."""
+    import torch
+    import torch.nn.functional as F
+    N, H, W, sig = cfg["N"], cfg["H"], cfg["W"], cfg["sigma"]
+    g = torch.Generator(device="cpu").manual_seed(seed)
+
+    def smooth(ch):
+        coarse = torch.randn(N, ch, H // 16 + 2, W // 16 + 2, generator=g).to(device)
+        return F.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True)
+
+    def flow():
+        f = smooth(2)
+        f[:, 0] *= 2.0 * sig / W
+        f[:, 1] *= 2.0 * sig / H
+        kick = (torch.rand(N, H, W, generator=g) < 0.01).to(device)  # >= 1% of pixels out of bounds
+        f[:, 0] = torch.where(kick, f[:, 0] + 2.5, f[:, 0])
+        return f.contiguous()
+
+    def seg():
+        lab = torch.randint(0, CH[1], (N, 1, (H + 7) // 8, (W + 7) // 8), generator=g).float().to(device)
+        lab = F.interpolate(lab, size=(H, W), mode="nearest").long()
+        return torch.zeros(N, CH[1], H, W, device=device).scatter_(1, lab, 1.0)
+
+    def rgb():
+        return (torch.rand(N, CH[0], H, W, generator=g) * 2 - 1).to(device)
+
+    return dict(f0=[rgb(), seg()], f1=[rgb(), seg()], ff=flow(), fb=flow(), mf=torch.sigmoid(smooth(1)),
+                mb=torch.sigmoid(smooth(1)), gos=[torch.randn(N, c, H, W, generator=g).to(device) for c in CH])
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc, self.path = None, f"/tmp/fwb_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.marks = {}
+
+    def mark(self, name):
+        self.marks[name] = time.time()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        import datetime
+        rows = []
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[1]), float(p[2]), float(p[3]), p[4], p[5], p[6], p[7], p[8]))
+            except Exception:
+                continue
+        os.unlink(self.path)
+        t0, t1 = self.marks.get("timed_start", 0), self.marks.get("timed_end", 1e18)
+        sel = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(sel) < 3:  # short timed region: widen to every sample taken while this bench was launching kernels
+            t0, t1 = self.marks.get("load_start", 0), self.marks.get("load_end", 1e18)
+            sel = [r for r in rows if t0 <= r[0] <= t1]
+            window = "warm-up + timed + per-kernel passes (timed region shorter than 3 samples)"
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        reasons = set()
+        for r in sel:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(r[1] for r in sel), "sm_max_mhz": sel[0][2],
+                "power_w_max": max(r[3] for r in sel), "reasons": sorted(reasons), "samples": len(sel), "window": window}
+
+
+# --------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_step(inp, pad="border"):
+    """The reference's own composition of torch ops (oracle/torch_ref.py restates utils/net_utils.py:93-114 and
+    nets/OpticalUnet.py:123-146), forward + backward, on the host cores."""
+    import torch
+    from oracle import torch_ref
+    leaves = [t.detach().clone().requires_grad_() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]]]
+    f0, f1, (ff, fb, mf, mb) = leaves[:2], leaves[2:4], leaves[4:]
+    outs = torch_ref.ref_warp_blend(f0, f1, ff, fb, mf, mb, padding_mode=pad, align_corners=False)
+    torch.autograd.backward(outs, inp["gos"])
+    return outs
+
+
+def time_cpu_reference(cfg, n_sample, min_seconds, min_reps, max_reps):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sub = dict(cfg, N=n_sample)
+    inp = make_inputs(sub, "cpu")
+    cpu_reference_step(inp)  # warm-up
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_reps and (len(times) < min_reps or time.perf_counter() - t_all < min_seconds):
+        t = time.perf_counter()
+        cpu_reference_step(inp)
+        times.append(time.perf_counter() - t)
+    pix = n_sample * cfg["H"] * cfg["W"]
+    return pix / statistics.median(times) / 1e9, cores, len(times)
+
+
+def run_reference_arm(args, cfg, rank, world):
+    """--impl reference: the reference path on the host cores (torch CPU, all threads), bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe = make_inputs(dict(cfg, N=1), "cpu")
+    cpu_reference_step(probe)
+    t = time.perf_counter()
+    cpu_reference_step(probe)
+    t1 = time.perf_counter() - t
+    n_s = int(max(1, min(cfg["N"], 90.0 / max((args.steps + args.warmup) * t1, 1e-9))))
+    inp = make_inputs(dict(cfg, N=n_s), "cpu")
+    for _ in range(args.warmup):
+        cpu_reference_step(inp)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(inp)
+    el = time.perf_counter() - t
+    pix = n_s * cfg["H"] * cfg["W"] * cfg["chain"]
+    val = pix * args.steps / el / 1e9
+    sample = f"{n_s} of {cfg['N']} clips per step ({cfg['H']}x{cfg['W']}, C={C_TOTAL}), torch {torch.__version__} CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "warp+blend fwd+bwd Gpix/s", "value": val, "unit": "Gpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------------------------- B200 arm
+class CabiStep:
+    """The three C-ABI entry points on preallocated device buffers (what the autograd op calls)."""
+
+    def __init__(self, inp, deterministic, pad="border"):
+        import torch
+        from deep_video_interpolation_extrapolation_b200 import _lib as L
+        from deep_video_interpolation_extrapolation_b200._problem import fill_grads, fill_problem
+        self.lib = L.load()
+        self.L = L
+        N, _, H, W = inp["ff"].shape
+        dev = inp["ff"].device
+        u5 = lambda t: t.unsqueeze(1)  # [N,C,H,W] -> [N,1,C,H,W]
+        self.keep = []
+        flows = [inp["ff"].unsqueeze(2), inp["fb"].unsqueeze(2)]
+        blends = [inp["mf"], inp["mb"]]
+        srcs = [[u5(a), u5(b)] for a, b in zip(inp["f0"], inp["f1"])]
+        self.outs = [torch.empty(N, 1, c, H, W, device=dev) for c in CH]
+        gos = [u5(g) for g in inp["gos"]]
+        self.g_srcs = [[torch.empty(N, 1, c, H, W, device=dev) for _ in range(2)] for c in CH]
+        self.g_flows = [torch.empty(N, 2, 1, H, W, device=dev) for _ in range(2)]
+        self.g_blends = [torch.empty(N, 1, H, W, device=dev) for _ in range(2)]
+        ptr, st = (lambda t: t.data_ptr()), (lambda t: t.stride())
+        self.p = fill_problem(N=N, T=1, H=H, W=W, flows=flows, gates=[None, None], blends=blends, signs=[-1.0, 1.0], srcs=srcs,
+                              outs=self.outs, padding_mode=L.FWB_PAD_BORDER if pad == "border" else L.FWB_PAD_ZEROS,
+                              align_corners=False, flags=L.FWB_FLAG_DETERMINISTIC if deterministic else 0, ptr=ptr, strides=st)
+        self.q = fill_grads(self.p, grad_outs=gos, grad_srcs=self.g_srcs, grad_flows=self.g_flows, grad_gates=[None, None],
+                            grad_blends=self.g_blends, ptr=ptr, strides=st)
+        self.keep += [flows, blends, srcs, gos]
+        self.ws_bytes = int(self.lib.fwb_workspace_bytes(ctypes.byref(self.p)))
+        self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def forward(self):
+        self.L.check(self.lib.fwb_warp_blend_forward(ctypes.byref(self.p), self.stream), "forward")
+
+    def backward_flow(self):
+        self.L.check(self.lib.fwb_warp_blend_backward_flow(ctypes.byref(self.p), ctypes.byref(self.q), self.ws.data_ptr(),
+                                                           self.ws_bytes, self.stream), "backward_flow")
+
+    def backward_src(self):
+        self.L.check(self.lib.fwb_warp_blend_backward_src(ctypes.byref(self.p), ctypes.byref(self.q), self.ws.data_ptr(),
+                                                          self.ws_bytes, self.stream), "backward_src")
+
+    def step(self):
+        self.forward()
+        self.backward_flow()
+        self.backward_src()
+
+
+def timed(fn, steps, warmup, sync):
+    import torch
+    for _ in range(warmup):
+        fn()
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    sync()
+    return a.elapsed_time(b) / 1e3  # seconds
+
+
+def run_b200_arm(args, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import deep_video_interpolation_extrapolation_b200 as P
+    from deep_video_interpolation_extrapolation_b200 import _lib
+    _lib.load()  # no fallback: fail loudly when the CUDA library is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    inp = make_inputs(cfg, dev, seed=rank)
+    ar_buf = torch.zeros(cfg["allreduce"], device=dev) if cfg["allreduce"] else None
+    chain = cfg["chain"]
+    step = CabiStep(inp, args.deterministic)
+
+    def one_step():
+        for _ in range(chain):  # config 3: K chained invocations per training step (runners/ExtraTrainer.py:254-310)
+            step.step()
+        if ar_buf is not None and world > 1:
+            dist.all_reduce(ar_buf)
+
+    pix_step = cfg["N"] * cfg["H"] * cfg["W"] * chain
+    if sampler:
+        sampler.mark("load_start")
+    # ---- headline: device-resident inputs, direct C-ABI launches, CUDA events, max over ranks
+    for _ in range(args.warmup):
+        one_step()
+    sync()
+    if sampler:
+        sampler.mark("timed_start")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        one_step()
+    b.record()
+    sync()
+    if sampler:
+        sampler.mark("timed_end")
+    el = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    el = float(el)
+    value = world * pix_step * args.steps / el / 1e9
+
+    # ---- per-kernel durations (same buffers, CUDA events on the launching stream)
+    kt = {}
+    ksteps = max(10, min(args.steps, 100))
+    for name, fn in (("forward", step.forward), ("backward_flow", step.backward_flow), ("backward_src", step.backward_src)):
+        kt[name] = timed(fn, ksteps, 3, sync) / ksteps
+
+    # ---- e2e: public autograd API, HOST (pinned) buffers, H2D + D2H inside the timed region
+    host_in = [t.cpu().pin_memory() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]] + inp["gos"]]
+    h2d = sum(t.numel() * 4 for t in host_in)
+    host_out = None
+
+    def e2e_step():
+        nonlocal host_out
+        d = [t.to(dev, non_blocking=True) for t in host_in]
+        leaves = [t.requires_grad_() for t in d[:8]]
+        outs = P.warp_blend(leaves[0:2], leaves[2:4], leaves[4], leaves[5], leaves[6], leaves[7], padding_mode="border",
+                            deterministic=args.deterministic)
+        torch.autograd.backward(outs, d[8:10])
+        res = list(outs) + [t.grad for t in leaves]
+        if host_out is None:
+            host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+        for h, t in zip(host_out, res):
+            h.copy_(t, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_el = torch.tensor([timed(e2e_step, e2e_steps, 2, sync)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_el, op=dist.ReduceOp.MAX)
+    d2h = sum(t.numel() * 4 for t in host_out)
+    e2e_val = world * cfg["N"] * cfg["H"] * cfg["W"] * e2e_steps / float(e2e_el) / 1e9
+    if sampler:
+        sampler.mark("load_end")
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        pix_launch = cfg["N"] * cfg["H"] * cfg["W"]
+        kernels = {k: {"ms": v * 1e3, "bytes_per_pixel": KERNEL_BYTES[k], "GBps": pix_launch * KERNEL_BYTES[k] / v / 1e9,
+                       "frac": pix_launch * KERNEL_BYTES[k] / v / 1e9 / peak} for k, v in kt.items()}
+        dom = max(kt, key=kt.get)
+        step_gbs = value / world * BYTES_PER_PIX  # per-GPU Gpix/s * B/pix = GB/s
+        out = {
+            "metric": "warp+blend fwd+bwd Gpix/s", "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
+                       "flow_sigma_px": cfg["sigma"], "chained_steps": chain, "padding_mode": "border", "align_corners": False,
+                       "deterministic": bool(args.deterministic), "parallelism": f"batch-sharded x{world}, no collective in the op",
+                       "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_pixel": KERNEL_BYTES[dom]},
+            "roofline_step": {"bytes_per_pixel": BYTES_PER_PIX, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
+            "kernels": kernels,
+            "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "deep_video_interpolation_extrapolation_b200.warp_blend + torch.autograd.backward, pinned host buffers"},
+            "gpu_launches": args.steps * chain * LAUNCHES_PER_STEP[bool(args.deterministic)],
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, reps = time_cpu_reference(cfg, cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1, 10.0, 3, 30)
+            ns = cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1
+            out["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": cores, "kind": "port",
+                                   "sample": f"{reps} reps of {ns} of {cfg['N']} clips, torch {torch.__version__} CPU restatement "
+                                             f"of the reference composition (oracle/torch_ref.py), fwd+bwd"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# launches of OUR kernels per step (forward 1, backward_flow 1, backward_src: see csrc/flowwarp_b200.cu)
+LAUNCHES_PER_STEP = {False: 1 + 1 + (4 + 1), True: 1 + 1 + (4 + 1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--sigma", type=float, default=None, help="override flow sigma in pixels")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = dict(CONFIGS[args.config])
+    if args.sigma is not None:
+        cfg["sigma"] = args.sigma
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+    else:
+        run_b200_arm(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

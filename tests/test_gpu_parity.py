@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA library (through the C-ABI / autograd op) against the CPU oracle, the committed golden
+vectors of the unmodified reference, and the stock torch grid_sample composition on the same device.
+
+Bars: sample indices + validity bits bit-exact; forward max|a-b| <= 1e-6*max|ref|;
+backward <= 1e-5*max|ref|; deterministic mode bit-exact run to run.
+"""
+import glob
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, BWD_TOL = 1e-6, 1e-5
+
+
+def relerr(a, ref):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    ref = ref.detach().cpu().numpy() if isinstance(ref, torch.Tensor) else ref
+    return float(np.abs(a.astype(np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def cu(a, grad=False):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda().requires_grad_(grad)
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import deep_video_interpolation_extrapolation_b200 as P
+    from deep_video_interpolation_extrapolation_b200 import _lib
+    _lib.load()  # fail loudly if the CUDA library is missing
+    return P
+
+
+def _golden(pattern):
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(here, pattern)))
+
+
+# ---------------------------------------------------------------- golden vectors of the reference
+@pytest.mark.parametrize("det", [False, True])
+@pytest.mark.parametrize("name", _golden("flowwrapper_*.npz"))
+def test_flowwrapper_vs_reference_golden(pkg, golden_dir, name, det):
+    z = np.load(os.path.join(golden_dir, name))
+    N, C, H, W = z["shape"]
+    s = z["seeds"]
+    x = cu(synth.rgb(s[0], N, H, W, C), True)
+    fl = cu(synth.flow(s[1], N, H, W, float(z["sigma"]), oob_frac=0.05), True)
+    go = cu(synth.grad(s[2], (N, C, H, W)))
+    out = pkg.FlowWrapper(deterministic=det)(x, fl)
+    out.backward(go)
+    assert relerr(out, z["out"]) <= FWD_TOL
+    assert relerr(x.grad, z["grad_x"]) <= BWD_TOL
+    assert relerr(fl.grad, z["grad_flow"]) <= BWD_TOL
+
+
+@pytest.mark.parametrize("det", [False, True])
+def test_warp_and_warp_back_vs_reference_golden(pkg, golden_dir, det):
+    fw = pkg.FlowWrapper(deterministic=det)
+    z = np.load(os.path.join(golden_dir, "warp_0.npz"))
+    N, C, T, H, W = z["shape"]
+    s = z["seeds"]
+    opt = types.SimpleNamespace(vid_length=int(T))
+    x, fl = cu(synth.rgb(s[0], N, H, W, C), True), cu(synth.flow(s[1], N, H, W, 2.0, T=T, oob_frac=0.05), True)
+    m = cu(synth.mask(s[2], N, H, W, T=T), True)
+    out = pkg.warp(x, fl, opt, fw, m)
+    out.backward(cu(synth.grad(s[3], (N, T, C, H, W))))
+    assert out.shape == (N, T, C, H, W)
+    assert relerr(out, z["out"]) <= FWD_TOL
+    assert relerr(x.grad, z["grad_x"]) <= BWD_TOL
+    assert relerr(fl.grad, z["grad_flow"]) <= BWD_TOL
+    assert relerr(m.grad, z["grad_mask"]) <= BWD_TOL
+
+    z = np.load(os.path.join(golden_dir, "warp_back_0.npz"))
+    s = z["seeds"]
+    xb = cu(np.stack([synth.rgb(s[0] + i, N, H, W, C) for i in range(T)], 1), True)
+    fl, m = cu(synth.flow(s[1], N, H, W, 2.0, T=T, oob_frac=0.05), True), cu(synth.mask(s[2], N, H, W, T=T), True)
+    out = pkg.warp_back(xb, fl, opt, fw, m)
+    out.backward(cu(synth.grad(s[3], (N, T, C, H, W))))
+    assert relerr(out, z["out"]) <= FWD_TOL
+    assert relerr(xb.grad, z["grad_x"]) <= BWD_TOL
+    assert relerr(fl.grad, z["grad_flow"]) <= BWD_TOL
+    assert relerr(m.grad, z["grad_mask"]) <= BWD_TOL
+
+
+@pytest.mark.parametrize("name", _golden("coordprobe_*.npz"))
+def test_coordinate_probe_bit_exact_vs_reference(pkg, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    fl, ref = z["flow"], z["out"]
+    M, _, H, W = fl.shape
+    if str(z["axis"]) == "x":
+        img = (np.arange(W) % 2).astype(np.float32).reshape(1, 1, 1, W).repeat(M, 0)
+    else:
+        img = (np.arange(H) % 2).astype(np.float32).reshape(1, 1, H, 1).repeat(M, 0)
+    out = pkg.FlowWrapper()(cu(img), cu(fl)).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), f"{(out != ref).sum()} of {out.size} differ"
+
+
+def test_config1_clip_vs_reference_golden(pkg, golden_dir):
+    z = np.load(os.path.join(golden_dir, "config1_clip.npz"))
+    s = z["seeds"]
+    N, H, W = 1, 128, 256
+    opt = types.SimpleNamespace(vid_length=1)
+    fw = pkg.FlowWrapper()
+    f1, f3, s1, s3 = (cu(a) for a in (synth.rgb(s[0], N, H, W), synth.rgb(s[1], N, H, W), synth.seg(s[2], N, H, W), synth.seg(s[3], N, H, W)))
+    flf, flb = cu(synth.flow(s[4], N, H, W, 8.0, T=1)), cu(synth.flow(s[5], N, H, W, 8.0, T=1))
+    mf, mb = cu(synth.mask(s[6], N, H, W, T=1)), cu(synth.mask(s[7], N, H, W, T=1))
+    rgb_f, seg_f = pkg.warp_multi([f1, s1], flf, opt, fw, mf)
+    rgb_b = pkg.warp_back(f3[:, None], flb, opt, fw, mb)
+    seg_b = pkg.warp_back(s3[:, None], flb, opt, fw, mb)
+    for name, o in dict(rgb_f=rgb_f, seg_f=seg_f, rgb_b=rgb_b, seg_b=seg_b).items():
+        assert relerr(o[..., ::4, ::4], z[name]) <= FWD_TOL, name
+
+
+# ---------------------------------------------------------------- indices / validity: bit-exact vs oracle
+@pytest.mark.parametrize("align", [False, True])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("shape", [(2, 37, 53), (1, 128, 256), (1, 1, 40), (1, 33, 1), (3, 64, 150)])
+def test_indices_and_validity_bit_exact(pkg, oracle, shape, pad, align):
+    N, H, W = shape
+    fl = synth.flow(7, N, H, W, 6.0, oob_frac=0.05)
+    g = synth.mask(8, N, H, W)
+    for sign in (-1.0, 1.0):
+        ref = oracle.sample_indices(fl, gate=g, sign=sign, padding_mode=pad, align_corners=align)
+        got = pkg.sample_indices(cu(fl), gate=cu(g), sign=sign, padding_mode=pad, align_corners=align)
+        for r, o, what in zip(ref, got, ("x0", "y0", "valid", "ix", "iy")):
+            o = o.cpu().numpy()
+            if r.dtype == np.float32:
+                assert np.array_equal(r.view(np.uint32), o.view(np.uint32)), what
+            else:
+                assert np.array_equal(r, o), what
+
+
+def test_indices_match_torch_cuda_grid_sample(pkg):
+    """The same parity-image probe as the golden one, against torch's own CUDA grid_sample on this device:
+    pins the kernel's coordinate arithmetic to ATen's CUDA binary bit for bit."""
+    from oracle import torch_ref
+    rng = np.random.default_rng(3)
+    for W in (7, 150, 256, 1000, 2047):
+        M = 64
+        img = cu((np.arange(W) % 2).astype(np.float32).reshape(1, 1, 1, W).repeat(M, 0))
+        fl = np.zeros((M, 2, 1, W), np.float32)
+        fl[:, 0] = rng.uniform(-1.2, 1.2, (M, 1, W)).astype(np.float32)
+        fl[:, 1] = -1.0
+        fl = cu(fl)
+        for align in (False, True):
+            ref = torch_ref.ref_flow_wrapper(img, fl, align_corners=align)
+            out = pkg.FlowWrapper(align_corners=align)(img, fl)
+            assert torch.equal(ref, out), (W, align, int((ref != out).sum()))
+
+
+# ---------------------------------------------------------------- fused op vs oracle and vs stock torch
+def _blend_inputs(N, H, W, Cs=(3, 20), sigma=8.0):
+    f0 = [synth.rgb(0, N, H, W, Cs[0])] + [synth.seg(1, N, H, W, c) for c in Cs[1:]]
+    f1 = [synth.rgb(10, N, H, W, Cs[0])] + [synth.seg(11, N, H, W, c) for c in Cs[1:]]
+    ff, fb = synth.flow(3, N, H, W, sigma), synth.flow(4, N, H, W, sigma)
+    mf, mb = synth.mask(2, N, H, W), synth.mask(12, N, H, W)
+    gos = [synth.grad(5 + i, a.shape) for i, a in enumerate(f0)]
+    return f0, f1, ff, fb, mf, mb, gos
+
+
+@pytest.mark.parametrize("det", [False, True])
+@pytest.mark.parametrize("pad,align", [("border", False), ("zeros", False), ("border", True), ("zeros", True)])
+def test_warp_blend_vs_oracle(pkg, oracle, pad, align, det):
+    N, H, W = 2, 48, 80
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    ref = oracle.forward(list(zip(f0, f1)), [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+    tff, tfb, tmf, tmb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+    outs = pkg.warp_blend(t0, t1, tff, tfb, tmf, tmb, padding_mode=pad, align_corners=align, deterministic=det)
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    for g in range(len(f0)):
+        assert relerr(outs[g], ref[g][:, 0]) <= FWD_TOL
+        assert relerr(t0[g].grad, rg["grad_srcs"][g][0][:, 0]) <= BWD_TOL
+        assert relerr(t1[g].grad, rg["grad_srcs"][g][1][:, 0]) <= BWD_TOL
+    assert relerr(tff.grad, rg["grad_flows"][0][:, :, 0]) <= BWD_TOL
+    assert relerr(tfb.grad, rg["grad_flows"][1][:, :, 0]) <= BWD_TOL
+    assert relerr(tmf.grad, rg["grad_blends"][0]) <= BWD_TOL
+    assert relerr(tmb.grad, rg["grad_blends"][1]) <= BWD_TOL
+
+
+@pytest.mark.parametrize("pad,align", [("border", False), ("zeros", True)])
+def test_warp_blend_vs_stock_torch_cuda(pkg, pad, align):
+    """Against the reference's own composition of torch ops, run on the same GPU (ATen grid_sampler_2d)."""
+    from oracle import torch_ref
+    N, H, W = 2, 64, 96
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    a0, a1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+    aff, afb, amf, amb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+    ref = torch_ref.ref_warp_blend(a0, a1, aff, afb, amf, amb, padding_mode=pad, align_corners=align)
+    torch.autograd.backward(ref, [cu(g) for g in gos])
+    t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+    tff, tfb, tmf, tmb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+    outs = pkg.warp_blend(t0, t1, tff, tfb, tmf, tmb, padding_mode=pad, align_corners=align)
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    for g in range(len(f0)):
+        assert relerr(outs[g], ref[g]) <= FWD_TOL
+        assert relerr(t0[g].grad, a0[g].grad) <= BWD_TOL
+        assert relerr(t1[g].grad, a1[g].grad) <= BWD_TOL
+    for a, b in ((tff, aff), (tfb, afb), (tmf, amf), (tmb, amb)):
+        assert relerr(a.grad, b.grad) <= BWD_TOL
+
+
+def test_bidirectional_warp_matches_opticalunet_restatement(pkg):
+    from oracle import torch_ref
+    N, H, W = 2, 40, 72
+    f0, f1 = cu(synth.rgb(0, N, H, W)), cu(synth.rgb(1, N, H, W))
+    ff, fb = cu(np.tanh(synth.flow(3, N, H, W, 6.0) * 4)), cu(np.tanh(synth.flow(4, N, H, W, 6.0) * 4))
+    mf, mb = cu(np.tanh(synth.grad(5, (N, 1, H, W)))), cu(np.tanh(synth.grad(6, (N, 1, H, W))))
+    ref = torch_ref.ref_bidirectional(f0, f1, ff, mf, fb, mb)
+    got = pkg.bidirectional_warp(f0, f1, ff, mf, fb, mb)
+    for r, g in zip(ref, got):
+        assert relerr(g, r) <= FWD_TOL
+
+
+# ---------------------------------------------------------------- known answers (SURVEY.md §8c ii)
+def test_known_answers(pkg):
+    N, C, H, W = 1, 2, 9, 11
+    x = cu(synth.rgb(0, N, H, W, C))
+    zero = torch.zeros(N, 2, H, W, device="cuda")
+    # zero flow + align_corners=True is the identity
+    assert relerr(pkg.FlowWrapper(align_corners=True)(x, zero), x) <= 1e-6
+    # integer-pixel flow 2k/(W-1) shifts by k pixels with zero fill (positive flow samples from the left)
+    k = 3
+    fl = zero.clone()
+    fl[:, 0] = 2.0 * k / (W - 1)
+    out = pkg.FlowWrapper(align_corners=True)(x, fl)
+    assert relerr(out[..., k:], x[..., : W - k]) <= 1e-5
+    assert float(out[..., : k - 1].abs().max()) <= 1e-5
+    # everything out of bounds: zeros padding -> 0, border padding -> edge replicate
+    fl = zero.clone()
+    fl[:, 0] = 5.0
+    assert float(pkg.FlowWrapper()(x, fl).abs().max()) == 0.0
+    out = pkg.FlowWrapper(padding_mode="border", align_corners=True)(x, fl)
+    assert torch.equal(out, x[..., :1].expand_as(x))
+    # half-pixel flow averages two neighbours
+    fl = zero.clone()
+    fl[:, 0] = 1.0 / (W - 1)
+    out = pkg.FlowWrapper(align_corners=True)(x, fl)
+    assert relerr(out[..., 1:], 0.5 * (x[..., 1:] + x[..., :-1])) <= 1e-5
+
+
+# ---------------------------------------------------------------- edge cases
+def test_strided_views_and_channel_counts(pkg, oracle):
+    N, T, H, W = 2, 3, 20, 36
+    big = synth.flow(1, N, H, W, 3.0, T=T + 2)
+    m = synth.mask(2, N, H, W, T=T + 2)
+    for C in (1, 3, 20, 23):
+        x = synth.rgb(C, N, H, W, C)
+        opt = types.SimpleNamespace(vid_length=T)
+        out = pkg.warp(cu(x), cu(big), opt, pkg.FlowWrapper(), cu(m))  # flow[:, :, :T] / mask[:, :T] are views
+        ref = oracle.forward([x], [big[:, :, :T]], gates=[m[:, :T]])[0]
+        assert relerr(out, ref) <= FWD_TOL
+    # non-unit W stride falls back to a contiguous copy
+    x = synth.rgb(9, N, H, W, 3)
+    flt = cu(np.ascontiguousarray(synth.flow(3, N, H, W, 3.0).transpose(0, 1, 3, 2))).transpose(2, 3)
+    out = pkg.FlowWrapper()(cu(x), flt)
+    ref = oracle.forward([x], [flt.cpu().numpy()])[0][:, 0]
+    assert relerr(out, ref) <= FWD_TOL
+
+
+def test_large_displacement_and_adversarial(pkg, oracle):
+    N, H, W = 1, 96, 160
+    x, go = synth.rgb(0, N, H, W, 5), synth.grad(1, (N, 5, H, W))
+    for fl in (synth.flow(2, N, H, W, 32.0), synth.adversarial_flow(3, N, H, W)):
+        for det in (False, True):
+            xt, ft = cu(x, True), cu(fl, True)
+            out = pkg.FlowWrapper(deterministic=det)(xt, ft)
+            out.backward(cu(go))
+            ref = oracle.forward([x], [fl])[0][:, 0]
+            rg = oracle.backward([x], [fl], [go])
+            assert relerr(out, ref) <= FWD_TOL
+            assert relerr(xt.grad, rg["grad_srcs"][0][0][:, 0]) <= BWD_TOL
+            assert relerr(ft.grad, rg["grad_flows"][0][:, :, 0]) <= BWD_TOL
+
+
+def test_deterministic_mode_bit_exact_run_to_run(pkg):
+    N, H, W = 4, 128, 256
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    runs = []
+    for _ in range(3):
+        t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+        outs = pkg.warp_blend(t0, t1, cu(ff), cu(fb), cu(mf), cu(mb), deterministic=True)
+        torch.autograd.backward(outs, [cu(g) for g in gos])
+        runs.append([t.grad.clone() for t in t0 + t1])
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+
+
+def test_empty_batch_and_errors(pkg):
+    x = torch.zeros(0, 3, 8, 8, device="cuda")
+    assert pkg.FlowWrapper()(x, torch.zeros(0, 2, 8, 8, device="cuda")).shape == (0, 3, 8, 8)
+    x = torch.zeros(2, 3, 8, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        pkg.FlowWrapper()(x, torch.zeros(3, 2, 8, 8, device="cuda"))  # batch mismatch
+    with pytest.raises(RuntimeError):
+        pkg.FlowWrapper()(x, torch.zeros(2, 3, 8, 8, device="cuda"))  # flow needs 2 channels
+    with pytest.raises(RuntimeError):
+        pkg.FlowWrapper()(x.cpu(), torch.zeros(2, 2, 8, 8))  # no CPU path
+    with pytest.raises(RuntimeError):
+        pkg.FlowWrapper()(x.double(), torch.zeros(2, 2, 8, 8, device="cuda").double())
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_full_size_properties_config2(pkg):
+    """BASELINE config 2 shape (16 x 23 x 256 x 512): properties that need no oracle."""
+    N, H, W = 16, 256, 512
+    g = torch.Generator(device="cuda").manual_seed(0)
+    f0 = [torch.rand(N, 3, H, W, device="cuda", generator=g) * 2 - 1, torch.rand(N, 20, H, W, device="cuda", generator=g)]
+    f1 = [torch.rand(N, 3, H, W, device="cuda", generator=g) * 2 - 1, torch.rand(N, 20, H, W, device="cuda", generator=g)]
+    ff, fb = cu(synth.flow(3, N, H, W, 8.0)), cu(synth.flow(4, N, H, W, 8.0))
+    mf, mb = cu(synth.mask(2, N, H, W)), cu(synth.mask(12, N, H, W))
+    out = pkg.warp_blend(f0, f1, ff, fb, mf, mb)
+    # linearity in the sources
+    out2 = pkg.warp_blend([2 * a for a in f0], [2 * a for a in f1], ff, fb, mf, mb)
+    for a, b in zip(out, out2):
+        assert relerr(b, 2 * a) <= 1e-6
+    # constant images + border padding + masks summing to 1 reproduce the constant
+    ones0 = [torch.ones_like(a) for a in f0]
+    o = pkg.warp_blend(ones0, ones0, ff, fb, mf, 1 - mf)
+    for a in o:
+        assert float((a - 1).abs().max()) <= 1e-6
+    # adjointness: <warp(x), g> == <x, warp^T(g)>  (the src-gradient kernel is the transpose of the forward)
+    x0 = [a.clone().requires_grad_() for a in f0]
+    x1 = [a.clone().requires_grad_() for a in f1]
+    outs = pkg.warp_blend(x0, x1, ff, fb, mf, mb)
+    gos = [torch.randn(a.shape, device="cuda", generator=g) for a in outs]
+    torch.autograd.backward(outs, gos)
+    lhs = sum(float((o.double() * q.double()).sum()) for o, q in zip(outs, gos))
+    rhs = sum(float((x.double() * x.grad.double()).sum()) for x in x0 + x1)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    # deterministic and atomic paths agree
+    y0 = [a.clone().requires_grad_() for a in f0]
+    y1 = [a.clone().requires_grad_() for a in f1]
+    torch.autograd.backward(pkg.warp_blend(y0, y1, ff, fb, mf, mb, deterministic=True), gos)
+    for a, b in zip(x0 + x1, y0 + y1):
+        assert relerr(a.grad, b.grad) <= BWD_TOL
