@@ -314,6 +314,11 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     el = float(el)
     value = world * pix_step * args.steps / el / 1e9
 
+    if args.profile:
+        if sampler:
+            sampler.stop()
+        print(f"profile run: {value:.3f} Gpix/s, {el / args.steps * 1e3:.3f} ms/step")
+        return
     # ---- per-kernel durations (same buffers, CUDA events on the launching stream)
     kt = {}
     ksteps = max(10, min(args.steps, 100))
@@ -399,6 +404,7 @@ def main():
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--sigma", type=float, default=None, help="override flow sigma in pixels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])

@@ -274,6 +274,9 @@ def flow_warp_blend(
             raise RuntimeError("both directions of a group must have the same channel count")
         csrcs.append(row)
 
+    if N == 0:  # nothing to launch (empty tensors have no storage to point the C-ABI at)
+        outs = [s.new_empty((0, T, s.shape[2], H, W)) for s in (row[0] for row in csrcs)]
+        return outs if five_d else [o.squeeze(1) for o in outs]
     cfg = _Cfg(D, G, signs, L.FWB_PAD_BORDER if padding_mode == "border" else L.FWB_PAD_ZEROS,
                bool(align_corners), bool(deterministic), N, T, H, W)
     flat = [*cflows, *cgates, *cblends, *[s for row in csrcs for s in row]]
