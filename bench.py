@@ -203,7 +203,7 @@ def run_reference_arm(args, cfg, rank, world):
 class CabiStep:
     """The three C-ABI entry points on preallocated device buffers (what the autograd op calls)."""
 
-    def __init__(self, inp, deterministic, pad="border"):
+    def __init__(self, inp, deterministic, pad="border", atomic_src=False):
         import torch
         from deep_video_interpolation_extrapolation_b200 import _lib as L
         from deep_video_interpolation_extrapolation_b200._problem import fill_grads, fill_problem
@@ -224,7 +224,8 @@ class CabiStep:
         ptr, st = (lambda t: t.data_ptr()), (lambda t: t.stride())
         self.p = fill_problem(N=N, T=1, H=H, W=W, flows=flows, gates=[None, None], blends=blends, signs=[-1.0, 1.0], srcs=srcs,
                               outs=self.outs, padding_mode=L.FWB_PAD_BORDER if pad == "border" else L.FWB_PAD_ZEROS,
-                              align_corners=False, flags=L.FWB_FLAG_DETERMINISTIC if deterministic else 0, ptr=ptr, strides=st)
+                              align_corners=False, flags=(L.FWB_FLAG_DETERMINISTIC if deterministic else 0) |
+                              (L.FWB_FLAG_ATOMIC_SRC if atomic_src else 0), ptr=ptr, strides=st)
         self.q = fill_grads(self.p, grad_outs=gos, grad_srcs=self.g_srcs, grad_flows=self.g_flows, grad_gates=[None, None],
                             grad_blends=self.g_blends, ptr=ptr, strides=st)
         self.keep += [flows, blends, srcs, gos]
@@ -283,7 +284,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     inp = make_inputs(cfg, dev, seed=rank)
     ar_buf = torch.zeros(cfg["allreduce"], device=dev) if cfg["allreduce"] else None
     chain = cfg["chain"]
-    step = CabiStep(inp, args.deterministic)
+    step = CabiStep(inp, args.deterministic, atomic_src=args.atomic_src)
 
     def one_step():
         for _ in range(chain):  # config 3: K chained invocations per training step (runners/ExtraTrainer.py:254-310)
@@ -402,6 +403,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--atomic-src", action="store_true", help="A/B: grad_src via the global-atomic scatter kernel")
     ap.add_argument("--sigma", type=float, default=None, help="override flow sigma in pixels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")

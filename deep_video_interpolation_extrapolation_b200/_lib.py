@@ -12,6 +12,7 @@ import os
 FWB_MAX_GROUPS = 4
 FWB_PAD_ZEROS, FWB_PAD_BORDER = 0, 1
 FWB_FLAG_DETERMINISTIC = 1
+FWB_FLAG_ATOMIC_SRC = 2  # grad_src by global atomics (ATen-style), for A/B measurements only
 
 _f32p = C.POINTER(C.c_float)
 i64 = C.c_int64

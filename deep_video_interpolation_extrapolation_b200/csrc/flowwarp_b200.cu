@@ -11,32 +11,23 @@
 
 #include "../../include/flowwarp_b200.h"
 #include "fwb_coords.cuh"
+#include "fwb_owner.cuh"
 
 namespace fwb {
 
-struct GradP {
-  const float* grad_out[FWB_MAX_GROUPS];
-  long long go_sn[FWB_MAX_GROUPS], go_st[FWB_MAX_GROUPS];
-  int go_sc[FWB_MAX_GROUPS], go_sh[FWB_MAX_GROUPS];
-  float* grad_src[FWB_MAX_GROUPS][2];
-  long long gs_sn[FWB_MAX_GROUPS][2], gs_st[FWB_MAX_GROUPS][2];
-  int gs_sc[FWB_MAX_GROUPS][2], gs_sh[FWB_MAX_GROUPS][2];
-  float* grad_flow[2];
-  long long gf_sn[2], gf_sc[2], gf_st[2], gf_sh[2];
-  float* grad_gate[2];
-  long long gg_sn[2], gg_st[2], gg_sh[2];
-  float* grad_blend[2];
-  long long gb_sn[2], gb_st[2], gb_sh[2];
-};
+// Thread -> pixel mapping.  A warp covers an 8x4 "micro-tile" (not 32x1): with rough flows the 32 taps of a
+// 32x1 row land on ~16 different source rows = ~16 L1 wavefronts per load; an 8x4 patch halves that.  A CTA
+// is 8 warps = 4x2 micro-tiles = 32x8 pixels.  The micro-tile is also the unit of the segment tables that
+// kernel 3 (owner gather) consumes.
+constexpr int BX = 32;  // CTA width in pixels
+constexpr int BY = 8;   // CTA height in pixels
+constexpr int NTHREADS = 256;
 
-struct Params {
-  Geo geo;
-  DirP dir[2];
-  GroupP grp[FWB_MAX_GROUPS];
-};
-
-constexpr int BX = 64;  // pixels of one row per CTA (2 warps wide)
-constexpr int BY = 4;   // rows per CTA
+__device__ __forceinline__ void thread_pixel(int& i, int& j) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  j = blockIdx.x * BX + (warp & 3) * MT_W + (lane & 7);
+  i = blockIdx.y * BY + (warp >> 2) * MT_H + (lane >> 3);
+}
 
 __device__ __forceinline__ float ldg_if(const float* p, bool ok) { return ok ? __ldg(p) : 0.0f; }
 
@@ -56,9 +47,10 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ s, int o, in
 // Kernel 1: fused forward warp (+gate) (+blend) for NDIRS directions and all channel groups.
 // ---------------------------------------------------------------------------------------------
 template <int NDIRS>
-__global__ void __launch_bounds__(BX* BY) fwd_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(NTHREADS) fwd_kernel(const __grid_constant__ Params P) {
   const Geo& G = P.geo;
-  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  int i, j;
+  thread_pixel(i, j);
   if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
 
@@ -110,7 +102,8 @@ __global__ void indices_kernel(const __grid_constant__ Params P, int d, int* __r
                                int* __restrict__ y0, uint8_t* __restrict__ valid, float* __restrict__ ix,
                                float* __restrict__ iy) {
   const Geo& G = P.geo;
-  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  int i, j;
+  thread_pixel(i, j);
   if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
   Tap k;
@@ -130,12 +123,21 @@ __global__ void indices_kernel(const __grid_constant__ Params P, int d, int* __r
 // which is ATen's grid_sampler_2d_backward accumulation with the common factors pulled out.
 // ---------------------------------------------------------------------------------------------
 template <int NDIRS>
-__global__ void __launch_bounds__(BX* BY) bwd_flow_kernel(const __grid_constant__ Params P,
-                                                          const __grid_constant__ GradP Q) {
+__global__ void __launch_bounds__(NTHREADS) bwd_flow_kernel(const __grid_constant__ Params P,
+                                                            const __grid_constant__ GradP Q, unsigned* __restrict__ gmax,
+                                                            const int ctot, const int want_grads) {
   const Geo& G = P.geo;
-  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-  if (j >= G.W || i >= G.H) return;
+  int i, j;
+  thread_pixel(i, j);
+  const bool active = j < G.W && i < G.H;
+  i = min(i, G.H - 1);  // lanes outside the image shadow an edge pixel (whole warps run the reductions below)
+  j = min(j, G.W - 1);
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
+  extern __shared__ unsigned s_gmax[];  // [NDIRS][ctot]  max |gOut*blend| of this CTA (float bits), for kernel 3
+  if (gmax) {
+    for (int k = threadIdx.x; k < NDIRS * ctot; k += NTHREADS) s_gmax[k] = 0u;
+    __syncthreads();
+  }
 
   Tap k[NDIRS];
   float gix[NDIRS], giy[NDIRS], gbl[NDIRS];
@@ -146,56 +148,73 @@ __global__ void __launch_bounds__(BX* BY) bwd_flow_kernel(const __grid_constant_
     gix[d] = giy[d] = gbl[d] = 0.0f;
     has_bl[d] = P.dir[d].blend != nullptr;
   }
+  int cbase = 0;
   for (int g = 0; g < G.n_groups; ++g) {
     const GroupP& R = P.grp[g];
-    if (!Q.grad_out[g]) continue;
-    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
-    const float* s[NDIRS];
-    int o[NDIRS];
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
-      o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
-    }
-#pragma unroll 2
-    for (int c = 0; c < R.C; ++c) {
-      const float gout = __ldcs(go + (long long)c * Q.go_sc[g]);
+    if (Q.grad_out[g]) {
+      const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
+      const float* s[NDIRS];
+      int o[NDIRS];
 #pragma unroll
       for (int d = 0; d < NDIRS; ++d) {
-        const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
-        const int sh = R.src_sh[d];
-        const unsigned v = k[d].valid;
-        const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
-        const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
-        float gw = gout;
-        if (has_bl[d]) {
-          const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
-          gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
-          gw = gout * k[d].blend;
+        s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
+        o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
+      }
+#pragma unroll 2
+      for (int c = 0; c < R.C; ++c) {
+        const float gout = __ldg(go + (long long)c * Q.go_sc[g]);
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          const float gw = has_bl[d] ? gout * k[d].blend : gout;
+          if (gmax) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(fabsf(gw)) : 0u);
+            if ((threadIdx.x & 31) == 0) atomicMax(&s_gmax[d * ctot + cbase + c], m);
+          }
+          if (want_grads) {
+            const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
+            const int sh = R.src_sh[d];
+            const unsigned v = k[d].valid;
+            const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
+            const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
+            if (has_bl[d]) {
+              const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
+              gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
+            }
+            gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
+            giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
+          }
         }
-        gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
-        giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
       }
     }
+    cbase += R.C;
   }
+  if (active && want_grads) {
 #pragma unroll
-  for (int d = 0; d < NDIRS; ++d) {
-    float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
-    if (P.dir[d].sign < 0.0f) {
-      gfx = -gfx;
-      gfy = -gfy;
+    for (int d = 0; d < NDIRS; ++d) {
+      float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
+      if (P.dir[d].sign < 0.0f) {
+        gfx = -gfx;
+        gfy = -gfy;
+      }
+      const bool gated = P.dir[d].gate != nullptr;
+      if (Q.grad_gate[d] && gated)
+        Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
+            __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
+      if (Q.grad_flow[d]) {
+        float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
+        o[0] = gated ? gfx * k[d].gate : gfx;
+        o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
+      }
+      if (Q.grad_blend[d] && has_bl[d])
+        Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
     }
-    const bool gated = P.dir[d].gate != nullptr;
-    if (Q.grad_gate[d] && gated)
-      Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
-          __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
-    if (Q.grad_flow[d]) {
-      float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
-      o[0] = gated ? gfx * k[d].gate : gfx;
-      o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
+  }
+  if (gmax) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < NDIRS * ctot; q += NTHREADS) {
+      const int d = q / ctot, c = q - d * ctot;
+      if (s_gmax[q]) atomicMax(&gmax[((size_t)d * gridDim.z + blockIdx.z) * ctot + c], s_gmax[q]);
     }
-    if (Q.grad_blend[d] && has_bl[d])
-      Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
   }
 }
 
@@ -217,10 +236,11 @@ __global__ void zero_rows_kernel(float* __restrict__ base, long long sn, long lo
 }
 
 template <int NDIRS>
-__global__ void __launch_bounds__(BX* BY) bwd_src_atomic_kernel(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(NTHREADS) bwd_src_atomic_kernel(const __grid_constant__ Params P,
                                                                 const __grid_constant__ GradP Q) {
   const Geo& G = P.geo;
-  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  int i, j;
+  thread_pixel(i, j);
   if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
   float w[NDIRS][4], bl[NDIRS];
@@ -423,7 +443,7 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   Params P;
   to_params(p, P);
   cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid = pixel_grid(p), block(BX, BY);
+  const dim3 grid = pixel_grid(p), block(NTHREADS);
   if (p->n_dirs == 2)
     fwd_kernel<2><<<grid, block, 0, s>>>(P);
   else
@@ -439,19 +459,23 @@ int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t
   if (p->N == 0) return 0;
   Params P;
   to_params(p, P);
-  indices_kernel<<<pixel_grid(p), dim3(BX, BY), 0, (cudaStream_t)stream>>>(P, d, x0, y0, valid, ix, iy);
+  indices_kernel<<<pixel_grid(p), dim3(NTHREADS), 0, (cudaStream_t)stream>>>(P, d, x0, y0, valid, ix, iy);
   return (int32_t)cudaGetLastError();
+}
+
+static int total_channels(const fwb_problem* p) {
+  int c = 0;
+  for (int g = 0; g < p->n_groups; ++g) c += p->grp[g].C;
+  return c;
 }
 
 size_t fwb_workspace_bytes(const fwb_problem* p) {
   if (validate(p)) return 0;
-  return 0;
+  return ws_layout(p->n_dirs, (long long)p->N * p->T, p->H, p->W, total_channels(p)).total;
 }
 
 int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
                                      size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   int rc = validate(p);
   if (rc) return rc;
   Params P;
@@ -461,18 +485,37 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   if (rc) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid = pixel_grid(p), block(BX, BY);
+  const int NT = p->N * p->T, ctot = total_channels(p);
+  // the segment tables + per-image max|gOut| that kernel 3 needs are produced whenever a workspace is supplied
+  const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W, ctot);
+  WsView ws = {};
+  const bool emit = workspace != nullptr && !(p->flags & FWB_FLAG_ATOMIC_SRC);
+  if (emit) {
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
+    ws = ws_view(workspace, L, NT, p->H, p->W, ctot);
+    const int nh = p->n_dirs * NT, ng = nh * ctot;
+    ws_init_kernel<<<((nh > ng ? nh : ng) + 255) / 256, 256, 0, s>>>(ws.hdr, nh, ws.gmax, ng);
+    const dim3 eg((p->W + 31) / 32, (p->H + 7) / 8, NT);
+    if (p->n_dirs == 2)
+      emit_kernel<2><<<eg, 256, 0, s>>>(P, ws);
+    else
+      emit_kernel<1><<<eg, 256, 0, s>>>(P, ws);
+  }
+  int want = 0;
+  for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
+  if (!want && !emit) return 0;
+  const dim3 grid = pixel_grid(p), block(NTHREADS);
+  const size_t sm = emit ? sizeof(unsigned) * p->n_dirs * ctot : 0;
+  if (sm > 48 * 1024) return FWB_E_SHAPE;
   if (p->n_dirs == 2)
-    bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
+    bwd_flow_kernel<2><<<grid, block, sm, s>>>(P, Q, emit ? ws.gmax : nullptr, ctot, want);
   else
-    bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+    bwd_flow_kernel<1><<<grid, block, sm, s>>>(P, Q, emit ? ws.gmax : nullptr, ctot, want);
   return (int32_t)cudaGetLastError();
 }
 
 int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   int rc = validate(p);
   if (rc) return rc;
   Params P;
@@ -482,6 +525,70 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
   if (rc) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  const int NT = p->N * p->T, ctot = total_channels(p);
+  if (!(p->flags & FWB_FLAG_ATOMIC_SRC)) {
+    // owner gather (deterministic): needs the tables the backward_flow call left in the workspace
+    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W, ctot);
+    if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
+    const WsView ws = ws_view(workspace, L, NT, p->H, p->W, ctot);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(bwd_src_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)own_smem_bytes(OWN_CMAX));
+      if (e != cudaSuccess) return (int32_t)e;
+      attr_set = true;
+    }
+    int cbase[FWB_MAX_GROUPS];
+    for (int gi = 0, c = 0; gi < p->n_groups; ++gi) {
+      cbase[gi] = c;
+      c += p->grp[gi].C;
+    }
+    for (int d = 0; d < p->n_dirs; ++d)
+      for (int shared = 0; shared < 2; ++shared) {
+        // channel runs of the groups that want grad_src for this direction with this T-sharing, <= OWN_CMAX per launch
+        OwnArgs A = {};
+        A.d = d;
+        A.tshared = shared;
+        auto flush = [&]() -> int32_t {
+          if (A.nseg == 0) return 0;
+          const dim3 grid((p->W + OT_W - 1) / OT_W, (p->H + OT_H - 1) / OT_H, shared ? p->N : NT);
+          bwd_src_owner_kernel<<<grid, OWN_THREADS, own_smem_bytes(A.ctot), s>>>(P, Q, ws, A);
+          A.nseg = 0;
+          A.ctot = 0;
+          return (int32_t)cudaGetLastError();
+        };
+        for (int gi = 0; gi < p->n_groups; ++gi) {
+          if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
+          const int is_shared = (Q.gs_st[gi][d] == 0 && p->T > 1) ? 1 : 0;
+          if (is_shared != shared) continue;
+          int c0 = 0;
+          while (c0 < p->grp[gi].C) {
+            const int take = min(p->grp[gi].C - c0, OWN_CMAX - A.ctot);
+            A.seg[A.nseg].g = gi;
+            A.seg[A.nseg].c0 = c0;
+            A.seg[A.nseg].c1 = c0 + take;
+            A.seg[A.nseg].cbase = cbase[gi] + c0;
+            A.nseg++;
+            A.ctot += take;
+            c0 += take;
+            if (A.ctot == OWN_CMAX || A.nseg == FWB_MAX_GROUPS)
+              if ((rc = flush())) return rc;
+          }
+        }
+        if ((rc = flush())) return rc;
+      }
+    // a group whose grad_out is NULL contributes nothing: its grad_src is zero
+    for (int gi = 0; gi < p->n_groups; ++gi)
+      for (int d = 0; d < p->n_dirs; ++d)
+        if (Q.grad_src[gi][d] && !Q.grad_out[gi]) {
+          const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
+          const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
+          zero_rows_kernel<<<zg, 256, 0, s>>>(Q.grad_src[gi][d], Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d],
+                                              Q.gs_sh[gi][d], p->N, Tn, p->grp[gi].C, p->H, p->W);
+        }
+    return (int32_t)cudaGetLastError();
+  }
+  // ---- global-atomic scatter (ATen-style; non-deterministic; kept for A/B measurements)
   for (int gi = 0; gi < p->n_groups; ++gi)
     for (int d = 0; d < p->n_dirs; ++d) {
       float* gs = Q.grad_src[gi][d];
@@ -491,7 +598,7 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
       zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d],
                                           p->N, Tn, p->grp[gi].C, p->H, p->W);
     }
-  const dim3 grid = pixel_grid(p), block(BX, BY);
+  const dim3 grid = pixel_grid(p), block(NTHREADS);
   if (p->n_dirs == 2)
     bwd_src_atomic_kernel<2><<<grid, block, 0, s>>>(P, Q);
   else

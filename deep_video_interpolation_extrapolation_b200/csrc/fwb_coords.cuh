@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/flowwarp_b200.h"
+
 namespace fwb {
 
 struct DirP {
@@ -111,5 +113,26 @@ __device__ __forceinline__ void compute_tap(const Geo& G, const DirP& D, int n, 
   k.valid = (unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
             ((unsigned)(xin1 && yin1) << 3);
 }
+
+struct GradP {
+  const float* grad_out[FWB_MAX_GROUPS];
+  long long go_sn[FWB_MAX_GROUPS], go_st[FWB_MAX_GROUPS];
+  int go_sc[FWB_MAX_GROUPS], go_sh[FWB_MAX_GROUPS];
+  float* grad_src[FWB_MAX_GROUPS][2];
+  long long gs_sn[FWB_MAX_GROUPS][2], gs_st[FWB_MAX_GROUPS][2];
+  int gs_sc[FWB_MAX_GROUPS][2], gs_sh[FWB_MAX_GROUPS][2];
+  float* grad_flow[2];
+  long long gf_sn[2], gf_sc[2], gf_st[2], gf_sh[2];
+  float* grad_gate[2];
+  long long gg_sn[2], gg_st[2], gg_sh[2];
+  float* grad_blend[2];
+  long long gb_sn[2], gb_st[2], gb_sh[2];
+};
+
+struct Params {
+  Geo geo;
+  DirP dir[2];
+  GroupP grp[FWB_MAX_GROUPS];
+};
 
 }  // namespace fwb

@@ -22,6 +22,15 @@ from ._problem import fill_grads, fill_problem
 
 Tensor = torch.Tensor
 
+# A/B switch for measurements: True routes grad_src through the ATen-style global-atomic scatter kernel instead of
+# the (deterministic) owner-gather kernel.  Not a fallback: both are CUDA kernels of this library.
+ATOMIC_SRC = False
+
+
+def _flags(cfg) -> int:
+    return (L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0) | (
+        L.FWB_FLAG_ATOMIC_SRC if (ATOMIC_SRC and not cfg.deterministic) else 0)
+
 
 @dataclass(frozen=True)
 class _Cfg:
@@ -81,7 +90,7 @@ class _WarpBlendFn(torch.autograd.Function):
             p = fill_problem(N=cfg.N, T=cfg.T, H=cfg.H, W=cfg.W, flows=flows, gates=gates, blends=blends,
                              signs=cfg.signs, srcs=srcs, outs=outs, padding_mode=cfg.padding_mode,
                              align_corners=cfg.align_corners,
-                             flags=L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0,
+                             flags=_flags(cfg),
                              ptr=_ptr, strides=_strides)
             L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), _stream_ptr(dev)), "fwb_warp_blend_forward")
         ctx.cfg = cfg
@@ -128,7 +137,7 @@ class _WarpBlendFn(torch.autograd.Function):
             p = fill_problem(N=N, T=T, H=H, W=W, flows=flows, gates=gates, blends=blends, signs=cfg.signs,
                              srcs=srcs, outs=None, padding_mode=cfg.padding_mode,
                              align_corners=cfg.align_corners,
-                             flags=L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0,
+                             flags=_flags(cfg),
                              ptr=_ptr, strides=_strides)
             q = fill_grads(p, grad_outs=gos, grad_srcs=g_srcs, grad_flows=g_flows, grad_gates=g_gates,
                            grad_blends=g_blends, ptr=_ptr, strides=_strides)

@@ -51,7 +51,8 @@ extern "C" {
 #define FWB_PAD_BORDER 1
 
 /* flags */
-#define FWB_FLAG_DETERMINISTIC 1u /* grad_src: owner-gather kernel only, bit-exact run to run */
+#define FWB_FLAG_DETERMINISTIC 1u /* grad_src must be bit-exact run to run (the default owner-gather kernel is) */
+#define FWB_FLAG_ATOMIC_SRC 2u    /* grad_src by global atomics (ATen-style scatter; non-deterministic; for A/B runs) */
 
 /* argument errors (negative return values) */
 #define FWB_E_NULL -1      /* a required pointer is NULL */
