@@ -124,20 +124,12 @@ __global__ void indices_kernel(const __grid_constant__ Params P, int d, int* __r
 // ---------------------------------------------------------------------------------------------
 template <int NDIRS>
 __global__ void __launch_bounds__(NTHREADS) bwd_flow_kernel(const __grid_constant__ Params P,
-                                                            const __grid_constant__ GradP Q, unsigned* __restrict__ gmax,
-                                                            const int ctot, const int want_grads) {
+                                                            const __grid_constant__ GradP Q) {
   const Geo& G = P.geo;
   int i, j;
   thread_pixel(i, j);
-  const bool active = j < G.W && i < G.H;
-  i = min(i, G.H - 1);  // lanes outside the image shadow an edge pixel (whole warps run the reductions below)
-  j = min(j, G.W - 1);
+  if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
-  extern __shared__ unsigned s_gmax[];  // [NDIRS][ctot]  max |gOut*blend| of this CTA (float bits), for kernel 3
-  if (gmax) {
-    for (int k = threadIdx.x; k < NDIRS * ctot; k += NTHREADS) s_gmax[k] = 0u;
-    __syncthreads();
-  }
 
   Tap k[NDIRS];
   float gix[NDIRS], giy[NDIRS], gbl[NDIRS];
@@ -148,73 +140,56 @@ __global__ void __launch_bounds__(NTHREADS) bwd_flow_kernel(const __grid_constan
     gix[d] = giy[d] = gbl[d] = 0.0f;
     has_bl[d] = P.dir[d].blend != nullptr;
   }
-  int cbase = 0;
   for (int g = 0; g < G.n_groups; ++g) {
     const GroupP& R = P.grp[g];
-    if (Q.grad_out[g]) {
-      const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
-      const float* s[NDIRS];
-      int o[NDIRS];
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
-        o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
-      }
-#pragma unroll 2
-      for (int c = 0; c < R.C; ++c) {
-        const float gout = __ldg(go + (long long)c * Q.go_sc[g]);
-#pragma unroll
-        for (int d = 0; d < NDIRS; ++d) {
-          const float gw = has_bl[d] ? gout * k[d].blend : gout;
-          if (gmax) {
-            const unsigned m = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(fabsf(gw)) : 0u);
-            if ((threadIdx.x & 31) == 0) atomicMax(&s_gmax[d * ctot + cbase + c], m);
-          }
-          if (want_grads) {
-            const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
-            const int sh = R.src_sh[d];
-            const unsigned v = k[d].valid;
-            const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
-            const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
-            if (has_bl[d]) {
-              const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
-              gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
-            }
-            gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
-            giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
-          }
-        }
-      }
-    }
-    cbase += R.C;
-  }
-  if (active && want_grads) {
+    if (!Q.grad_out[g]) continue;
+    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
+    const float* s[NDIRS];
+    int o[NDIRS];
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {
-      float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
-      if (P.dir[d].sign < 0.0f) {
-        gfx = -gfx;
-        gfy = -gfy;
+      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
+      o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
+    }
+#pragma unroll 2
+    for (int c = 0; c < R.C; ++c) {
+      const float gout = __ldg(go + (long long)c * Q.go_sc[g]);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
+        const int sh = R.src_sh[d];
+        const unsigned v = k[d].valid;
+        const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
+        const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
+        float gw = gout;
+        if (has_bl[d]) {
+          const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
+          gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
+          gw = gout * k[d].blend;
+        }
+        gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
+        giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
       }
-      const bool gated = P.dir[d].gate != nullptr;
-      if (Q.grad_gate[d] && gated)
-        Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
-            __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
-      if (Q.grad_flow[d]) {
-        float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
-        o[0] = gated ? gfx * k[d].gate : gfx;
-        o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
-      }
-      if (Q.grad_blend[d] && has_bl[d])
-        Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
     }
   }
-  if (gmax) {
-    __syncthreads();
-    for (int q = threadIdx.x; q < NDIRS * ctot; q += NTHREADS) {
-      const int d = q / ctot, c = q - d * ctot;
-      if (s_gmax[q]) atomicMax(&gmax[((size_t)d * gridDim.z + blockIdx.z) * ctot + c], s_gmax[q]);
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
+    if (P.dir[d].sign < 0.0f) {
+      gfx = -gfx;
+      gfy = -gfy;
     }
+    const bool gated = P.dir[d].gate != nullptr;
+    if (Q.grad_gate[d] && gated)
+      Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
+          __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
+    if (Q.grad_flow[d]) {
+      float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
+      o[0] = gated ? gfx * k[d].gate : gfx;
+      o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
+    }
+    if (Q.grad_blend[d] && has_bl[d])
+      Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
   }
 }
 
@@ -463,15 +438,9 @@ int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t
   return (int32_t)cudaGetLastError();
 }
 
-static int total_channels(const fwb_problem* p) {
-  int c = 0;
-  for (int g = 0; g < p->n_groups; ++g) c += p->grp[g].C;
-  return c;
-}
-
 size_t fwb_workspace_bytes(const fwb_problem* p) {
   if (validate(p)) return 0;
-  return ws_layout(p->n_dirs, (long long)p->N * p->T, p->H, p->W, total_channels(p)).total;
+  return ws_layout(p->n_dirs, (long long)p->N * p->T, p->H, p->W).total;
 }
 
 int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
@@ -485,16 +454,14 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   if (rc) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int NT = p->N * p->T, ctot = total_channels(p);
-  // the segment tables + per-image max|gOut| that kernel 3 needs are produced whenever a workspace is supplied
-  const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W, ctot);
-  WsView ws = {};
-  const bool emit = workspace != nullptr && !(p->flags & FWB_FLAG_ATOMIC_SRC);
-  if (emit) {
+  const int NT = p->N * p->T;
+  // the segment tables kernel 3 needs are produced whenever a workspace is supplied
+  if (workspace && !(p->flags & FWB_FLAG_ATOMIC_SRC)) {
+    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
-    ws = ws_view(workspace, L, NT, p->H, p->W, ctot);
-    const int nh = p->n_dirs * NT, ng = nh * ctot;
-    ws_init_kernel<<<((nh > ng ? nh : ng) + 255) / 256, 256, 0, s>>>(ws.hdr, nh, ws.gmax, ng);
+    const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
+    const int nh = p->n_dirs * NT;
+    ws_init_kernel<<<(nh + 255) / 256, 256, 0, s>>>(ws.hdr, nh);
     const dim3 eg((p->W + 31) / 32, (p->H + 7) / 8, NT);
     if (p->n_dirs == 2)
       emit_kernel<2><<<eg, 256, 0, s>>>(P, ws);
@@ -503,14 +470,13 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   }
   int want = 0;
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
-  if (!want && !emit) return 0;
-  const dim3 grid = pixel_grid(p), block(NTHREADS);
-  const size_t sm = emit ? sizeof(unsigned) * p->n_dirs * ctot : 0;
-  if (sm > 48 * 1024) return FWB_E_SHAPE;
-  if (p->n_dirs == 2)
-    bwd_flow_kernel<2><<<grid, block, sm, s>>>(P, Q, emit ? ws.gmax : nullptr, ctot, want);
-  else
-    bwd_flow_kernel<1><<<grid, block, sm, s>>>(P, Q, emit ? ws.gmax : nullptr, ctot, want);
+  if (want) {
+    const dim3 grid = pixel_grid(p), block(NTHREADS);
+    if (p->n_dirs == 2)
+      bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
+    else
+      bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+  }
   return (int32_t)cudaGetLastError();
 }
 
@@ -525,36 +491,34 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
   if (rc) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int NT = p->N * p->T, ctot = total_channels(p);
+  const int NT = p->N * p->T;
   if (!(p->flags & FWB_FLAG_ATOMIC_SRC)) {
     // owner gather (deterministic): needs the tables the backward_flow call left in the workspace
-    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W, ctot);
+    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
     if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
-    const WsView ws = ws_view(workspace, L, NT, p->H, p->W, ctot);
+    const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(bwd_src_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)own_smem_bytes(OWN_CMAX));
+                                           (int)own_smem_bytes(OWN_MAXGRP));
       if (e != cudaSuccess) return (int32_t)e;
       attr_set = true;
     }
-    int cbase[FWB_MAX_GROUPS];
-    for (int gi = 0, c = 0; gi < p->n_groups; ++gi) {
-      cbase[gi] = c;
-      c += p->grp[gi].C;
-    }
     for (int d = 0; d < p->n_dirs; ++d)
       for (int shared = 0; shared < 2; ++shared) {
-        // channel runs of the groups that want grad_src for this direction with this T-sharing, <= OWN_CMAX per launch
+        // channel runs of the groups that want grad_src for this direction with this T-sharing,
+        // <= 4*OWN_MAXGRP channels per launch
         OwnArgs A = {};
         A.d = d;
         A.tshared = shared;
         auto flush = [&]() -> int32_t {
           if (A.nseg == 0) return 0;
+          A.ngrp = (A.nchan + 3) / 4;
+          const int nwarps = A.ngrp < 4 ? 4 : A.ngrp;
           const dim3 grid((p->W + OT_W - 1) / OT_W, (p->H + OT_H - 1) / OT_H, shared ? p->N : NT);
-          bwd_src_owner_kernel<<<grid, OWN_THREADS, own_smem_bytes(A.ctot), s>>>(P, Q, ws, A);
+          bwd_src_owner_kernel<<<grid, nwarps * 32, own_smem_bytes(A.ngrp), s>>>(P, Q, ws, A);
           A.nseg = 0;
-          A.ctot = 0;
+          A.nchan = 0;
           return (int32_t)cudaGetLastError();
         };
         for (int gi = 0; gi < p->n_groups; ++gi) {
@@ -563,15 +527,14 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
           if (is_shared != shared) continue;
           int c0 = 0;
           while (c0 < p->grp[gi].C) {
-            const int take = min(p->grp[gi].C - c0, OWN_CMAX - A.ctot);
+            const int take = min(p->grp[gi].C - c0, 4 * OWN_MAXGRP - A.nchan);
             A.seg[A.nseg].g = gi;
             A.seg[A.nseg].c0 = c0;
             A.seg[A.nseg].c1 = c0 + take;
-            A.seg[A.nseg].cbase = cbase[gi] + c0;
             A.nseg++;
-            A.ctot += take;
+            A.nchan += take;
             c0 += take;
-            if (A.ctot == OWN_CMAX || A.nseg == FWB_MAX_GROUPS)
+            if (A.nchan == 4 * OWN_MAXGRP || A.nseg == FWB_MAX_GROUPS)
               if ((rc = flush())) return rc;
           }
         }

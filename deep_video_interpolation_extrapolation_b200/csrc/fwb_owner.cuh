@@ -1,20 +1,21 @@
 // fwb_owner.cuh — kernel 3 (gradient w.r.t. the sources) as an OWNER GATHER, plus the segment tables it reads.
 //
-// ATen's grid_sampler_2d_backward scatters w*gOut with one global atomicAdd per tap per channel
-// (184 atomics per pixel for the headline config; measured 0.35 T adds/s on B200 = 1.1 ms).  Here each CTA
-// OWNS a 32x16 tile of grad_src and pulls in every contribution that lands in it:
-//   * kernel 2 leaves, per 8x4 output micro-tile (one warp), the bounding box of its in-image taps
-//     (8 B record) and appends pixels that stray from their micro-tile ("outliers", e.g. the border-clipped
-//     ones) to a per-image list, plus the min/max micro-tile displacement per image;
-//   * an owner CTA scans the records whose displacement window can reach its tile, and for the hits
-//     recomputes the taps and accumulates w*gOut into shared memory;
-//   * accumulation is 32-bit FIXED POINT with native shared-memory integer atomics (ATOMS.ADD; fp32
-//     shared atomicAdd is a CAS loop on sm_100a): integer addition is associative, so the result is
-//     bit-exact run to run no matter how warps interleave — the deterministic mode costs nothing.
-//     The scale is a power of two chosen per (tile, channel) from max|gOut| over the contributing pixels
-//     and the largest fan-in of the tile, so the sum cannot overflow and the quantum is <= 2^-29 of it.
-//   * the tile is written once with plain coalesced stores: no memset, no global atomics, algorithmic
-//     DRAM traffic (8C B/pixel written once).
+// ATen's grid_sampler_2d_backward scatters w*gOut with one global atomicAdd per tap per channel (184 atomics
+// per pixel in the headline config; measured ~0.35 T adds/s on B200 = 1.1 ms, and L2 atomics top out near
+// 0.6 T float-adds/s even as red.v4).  Here each CTA OWNS a 32x16 tile of grad_src and pulls in every
+// contribution that lands in it — no memset, no global atomics, the tile is written once (8C B/pixel):
+//   * emit_kernel leaves, per 8x4 output micro-tile (one warp), the bounding box of its in-image taps (8 B
+//     record), appends the few pixels that stray far from their micro-tile ("outliers", e.g. border-clipped
+//     ones) to a per-image list, and records the min/max micro-tile displacement per image;
+//   * an owner CTA scans the records whose displacement window can reach its tile, sorts the hits, and
+//     compacts — in a fixed order — the candidate pixels that really have a tap inside the tile into 16-byte
+//     tap records in shared memory (phase 1);
+//   * phase 2: warp w owns the float4 accumulators of channels 4w..4w+3 for the whole tile and walks the
+//     records: 4 coalesced loads of gOut, then per tap one LDS.128 / 4 FFMA / STS.128 — a quarter of the
+//     shared-memory instructions of a per-channel scatter, and no atomics at all (fp32 shared atomicAdd is a
+//     CAS loop on sm_100a).  Lanes of one batch that hit the same pixel are serialised by a precomputed rank.
+//   * every order (hits, records, ranks, frames) is fixed, so the fp32 result is bit-exact run to run: the
+//     deterministic mode is simply the default path.
 #pragma once
 #include "fwb_coords.cuh"
 
@@ -22,19 +23,11 @@ namespace fwb {
 
 constexpr int MT_W = 8, MT_H = 4;       // micro-tile = the 32 output pixels of one warp
 constexpr int OUTLIER_R = 12;           // a pixel farther than this (px) from its micro-tile's anchor displacement is an outlier
-#ifndef FWB_OT_W
-#define FWB_OT_W 32
-#endif
-#ifndef FWB_OT_H
-#define FWB_OT_H 32
-#endif
-constexpr int OT_W = FWB_OT_W, OT_H = FWB_OT_H;  // owner tile (source pixels)
-constexpr int OT_PITCH = OT_W + 8;      // == 8 (mod 32): the 4 rows of an undistorted 8x4 micro-tile hit 32 distinct banks
-constexpr int OT_WORDS = OT_PITCH * OT_H;
-constexpr int OWN_THREADS = 512;
-constexpr int HITCAP = 1024;            // hit-list chunk
-constexpr int OWN_CMAX = 40;            // channels per launch (shared-memory accumulators: OT_WORDS*4 B per channel)
-constexpr int HEADROOM0 = 6;            // fixed-point integer bits reserved for the fan-in (2^6 contributions per pixel)
+constexpr int OT_W = 32, OT_H = 16;     // owner tile (source pixels)
+constexpr int OT_PIX = OT_W * OT_H;
+constexpr int OWN_MAXGRP = 8;           // float4 channel groups (= phase-2 warps) per launch: 32 channels
+constexpr int OWN_RC = 768;             // tap records per chunk
+constexpr int OWN_HITCAP = 512;         // hit-list chunk
 
 struct WsHeader {  // one per (direction, n*T+t)
   int dxmin, dxmax, dymin, dymax;  // range of the micro-tile anchor displacements (pixels)
@@ -43,30 +36,26 @@ struct WsHeader {  // one per (direction, n*T+t)
 };
 
 struct WsView {
-  WsHeader* hdr;        // [D][NT]
-  short4* tab;          // [D][NT][mth][mtw]   {xmin, xmax, ymin, ymax} of the in-image taps of inlier pixels
-  int2* outl;           // [D][NT][cap]        {i*W+j, (y0<<16)|(x0&0xffff)}
-  unsigned* gmax;       // [D][NT][ctot]       max |gOut*blend| as float bits, per image and channel (kernel 2)
+  WsHeader* hdr;  // [D][NT]
+  short4* tab;    // [D][NT][mth][mtw]   {xmin, xmax, ymin, ymax} of the in-image taps of inlier pixels
+  int2* outl;     // [D][NT][cap]        {i*W+j, (y0<<16)|(x0&0xffff)}
   int mtw, mth;
-  long long cap;        // H*W
-  int NT, ctot;
+  long long cap;  // H*W
+  int NT;
 };
 
 struct WsLayout {
-  size_t hdr_off, tab_off, outl_off, gmax_off, total;
+  size_t hdr_off, tab_off, outl_off, total;
   int mtw, mth;
 };
 
-static inline WsLayout ws_layout(int D, long long NT, int H, int W, int ctot) {
+static inline WsLayout ws_layout(int D, long long NT, int H, int W) {
   WsLayout L;
   L.mtw = (W + MT_W - 1) / MT_W;
   L.mth = (H + MT_H - 1) / MT_H;
   size_t o = 0;
   L.hdr_off = o;
   o += sizeof(WsHeader) * (size_t)D * NT;
-  o = (o + 255) & ~(size_t)255;
-  L.gmax_off = o;
-  o += sizeof(unsigned) * (size_t)D * NT * ctot;
   o = (o + 255) & ~(size_t)255;
   L.tab_off = o;
   o += sizeof(short4) * (size_t)D * NT * L.mtw * L.mth;
@@ -77,30 +66,26 @@ static inline WsLayout ws_layout(int D, long long NT, int H, int W, int ctot) {
   return L;
 }
 
-static inline WsView ws_view(void* base, const WsLayout& L, int NT, int H, int W, int ctot) {
+static inline WsView ws_view(void* base, const WsLayout& L, int NT, int H, int W) {
   WsView v;
   char* b = (char*)base;
   v.hdr = (WsHeader*)(b + L.hdr_off);
   v.tab = (short4*)(b + L.tab_off);
   v.outl = (int2*)(b + L.outl_off);
-  v.gmax = (unsigned*)(b + L.gmax_off);
   v.mtw = L.mtw;
   v.mth = L.mth;
   v.cap = (long long)H * W;
   v.NT = NT;
-  v.ctot = ctot;
   return v;
 }
 
-// header + gmax are contiguous at the start of the workspace: one init kernel
-__global__ void ws_init_kernel(WsHeader* hdr, int n, unsigned* gmax, int ng) {
+__global__ void ws_init_kernel(WsHeader* hdr, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) {
     hdr[k].dxmin = hdr[k].dymin = 0x7fffffff;
     hdr[k].dxmax = hdr[k].dymax = -0x7fffffff;
     hdr[k].n_outliers = 0;
   }
-  if (k < ng) gmax[k] = 0u;
 }
 
 // Whole-warp classification of one micro-tile.  `has` = this lane's pixel is inside the image and has at
@@ -195,203 +180,331 @@ __global__ void __launch_bounds__(256) emit_kernel(const __grid_constant__ Param
 }
 
 struct OwnSeg {  // a run of channels of one group handled by this launch
-  int g, c0, c1, cbase;  // cbase = index of channel c0 in the problem-wide channel numbering (gmax table)
+  int g, c0, c1;
 };
 struct OwnArgs {
-  int d;         // direction
-  int tshared;   // grad_src of these groups has T-stride 0: one tile accumulates all T frames
-  int nseg, ctot;
+  int d;        // direction
+  int tshared;  // grad_src of these groups has T-stride 0: one tile accumulates all T frames
+  int nseg, nchan, ngrp;
   OwnSeg seg[FWB_MAX_GROUPS];
 };
 
-// One candidate pixel (lane) against the owner tile: fan-in count + fixed-point accumulation of w*gOut.
-__device__ __forceinline__ void own_pixel(const Params& P, const GradP& Q, const OwnArgs& A, int n, int t, int i, int j,
-                                          bool mine, const Tap& k, int sx0, int sy0, int* s_acc, int* s_cnt,
-                                          const float* s_scale) {
-  const int d = A.d;
-  const int px = k.x0 - sx0, py = k.y0 - sy0;
-  const bool cx0 = (unsigned)px < (unsigned)OT_W, cx1 = (unsigned)(px + 1) < (unsigned)OT_W;
-  const bool cy0 = (unsigned)py < (unsigned)OT_H, cy1 = (unsigned)(py + 1) < (unsigned)OT_H;
-  const bool in0 = mine && (k.valid & 1u) && cx0 && cy0, in1 = mine && (k.valid & 2u) && cx1 && cy0;
-  const bool in2 = mine && (k.valid & 4u) && cx0 && cy1, in3 = mine && (k.valid & 8u) && cx1 && cy1;
-  const bool any = in0 || in1 || in2 || in3;
-  if (!__any_sync(0xffffffffu, any)) return;
-  const int pos = py * OT_PITCH + px;
-  const bool has_bl = P.dir[d].blend != nullptr;
-  if (in0) atomicAdd(&s_cnt[pos], 1);
-  if (in1) atomicAdd(&s_cnt[pos + 1], 1);
-  if (in2) atomicAdd(&s_cnt[pos + OT_PITCH], 1);
-  if (in3) atomicAdd(&s_cnt[pos + OT_PITCH + 1], 1);
-  const float w0 = __fmul_rn(k.ux, k.uy), w1 = __fmul_rn(k.tx, k.uy), w2 = __fmul_rn(k.ux, k.ty), w3 = __fmul_rn(k.tx, k.ty);
-  int cc = 0;
-  for (int s = 0; s < A.nseg; ++s) {
-    const int g = A.seg[s].g;
-    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
-#pragma unroll 4
-    for (int c = A.seg[s].c0; c < A.seg[s].c1; ++c, ++cc) {
-      float gw = 0.0f;
-      if (any) {
-        gw = __ldg(go + (long long)c * Q.go_sc[g]);
-        if (has_bl) gw = __fmul_rn(gw, k.blend);
-      }
-      const float gs = gw * s_scale[cc];  // exact: the scale is a power of two
-      int* a = s_acc + cc * OT_WORDS + pos;
-      if (in0) atomicAdd(a, __float2int_rn(w0 * gs));
-      if (in1) atomicAdd(a + 1, __float2int_rn(w1 * gs));
-      if (in2) atomicAdd(a + OT_PITCH, __float2int_rn(w2 * gs));
-      if (in3) atomicAdd(a + OT_PITCH + 1, __float2int_rn(w3 * gs));
-    }
+struct OwnSmem {
+  float4* acc;     // [ngrp][OT_PIX]
+  uint4* rec;      // [OWN_RC]  {tx bits, ty bits, packed, (i<<16)|j};  packed = (px+1) | (py+1)<<6 | inbits<<12 | rank<<16
+  float* blend;    // [OWN_RC]
+  int* hits;       // [OWN_HITCAP] unsorted
+  int* hits2;      // [OWN_HITCAP] sorted
+  int* bmax;       // [OWN_RC/32] largest rank of each batch of 32 records
+  int* wcnt;       // [32] per-warp record counts of a phase-1 round
+  int* misc;       // [4]
+};
+
+// sort the `n` distinct values of s.hits into s.hits2 (rank by counting; n <= OWN_HITCAP)
+__device__ __forceinline__ void own_sort_hits(const OwnSmem& s, int n) {
+  for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    const int v = s.hits[a];
+    int r = 0;
+    for (int b = 0; b < n; ++b) r += (s.hits[b] < v);
+    s.hits2[r] = v;
   }
 }
 
-__global__ void __launch_bounds__(OWN_THREADS) bwd_src_owner_kernel(const __grid_constant__ Params P,
-                                                                    const __grid_constant__ GradP Q, const WsView ws,
-                                                                    const __grid_constant__ OwnArgs A) {
-  extern __shared__ int smem[];
+// phase 1 (one round): every warp brings one candidate lane-set; lanes with a tap inside the tile are appended
+// to the record chunk in (warp, lane) order.  All threads of the CTA must call this.  Returns the new count.
+__device__ __forceinline__ int own_append(const OwnSmem& s, int nrec, bool take, const Tap& k, int px, int py, unsigned bits,
+                                          int i, int j) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (lane == 0) s.wcnt[warp] = __popc(m);
+  __syncthreads();
+  int base = nrec, total = 0;
+  for (int w = 0; w < nw; ++w) {
+    const int c = s.wcnt[w];
+    if (w < warp) base += c;
+    total += c;
+  }
+  if (take) {
+    const int idx = base + __popc(m & ((1u << lane) - 1u));
+    s.rec[idx] = make_uint4(__float_as_uint(k.tx), __float_as_uint(k.ty),
+                            (unsigned)(px + 1) | ((unsigned)(py + 1) << 6) | (bits << 12), ((unsigned)i << 16) | (unsigned)j);
+    s.blend[idx] = k.blend;
+  }
+  __syncthreads();
+  return nrec + total;
+}
+
+// which taps of pixel tap `k` fall inside the owner tile at (sx0, sy0)
+__device__ __forceinline__ unsigned own_bits(const Tap& k, bool mine, int sx0, int sy0, int& px, int& py) {
+  px = k.x0 - sx0;
+  py = k.y0 - sy0;
+  if (!mine) return 0u;
+  const bool cx0 = (unsigned)px < (unsigned)OT_W, cx1 = (unsigned)(px + 1) < (unsigned)OT_W;
+  const bool cy0 = (unsigned)py < (unsigned)OT_H, cy1 = (unsigned)(py + 1) < (unsigned)OT_H;
+  unsigned b = 0u;
+  if ((k.valid & 1u) && cx0 && cy0) b |= 1u;
+  if ((k.valid & 2u) && cx1 && cy0) b |= 2u;
+  if ((k.valid & 4u) && cx0 && cy1) b |= 4u;
+  if ((k.valid & 8u) && cx1 && cy1) b |= 8u;
+  return b;
+}
+
+struct OwnChan {  // the (up to) 4 channels a phase-2 warp owns
+  const float* gp[4];  // grad_out plane base for (n, c); + t*gst + i*gsh + j
+  long long gst[4];
+  int gsh[4];
+  float* op[4];        // grad_src plane base for (n, [t], c)
+  int osh[4];
+  bool ok[4];
+};
+
+// phases 1.5 + 2 over the current record chunk (all threads call; frame t)
+__device__ __forceinline__ void own_flush(const OwnSmem& s, int nrec, int t, int ngrp, const OwnChan& ch, bool has_bl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nb = (nrec + 31) >> 5;
+  // ---- phase 1.5: lanes of one batch that target the same pixel get ranks 0,1,2..; they are applied in turns
+  for (int b = warp; b < nb; b += nw) {
+    const int idx = b * 32 + lane;
+    const bool valid = idx < nrec;
+    const unsigned pk = valid ? s.rec[idx].z : 0u;
+    const unsigned key = valid ? (pk & 0xfffu) : (0x10000u | (unsigned)lane);
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    if (valid) s.rec[idx].z = pk | ((unsigned)rank << 16);
+    const int mr = __reduce_max_sync(0xffffffffu, rank);
+    if (lane == 0) s.bmax[b] = mr;
+  }
+  __syncthreads();
+  // ---- phase 2: warp w accumulates channels 4w..4w+3 of every record
+  if (warp < ngrp) {
+    float4* acc = s.acc + warp * OT_PIX;
+    uint4 r_n = make_uint4(0, 0, 0, 0);
+    float g_n[4] = {0.f, 0.f, 0.f, 0.f};
+    auto load = [&](int b) {
+      const int idx = b * 32 + lane;
+      const bool valid = idx < nrec;
+      r_n = valid ? s.rec[idx] : make_uint4(0, 0, 0, 0);
+      const int i = (int)(r_n.w >> 16), j = (int)(r_n.w & 0xffffu);
+      const float bl = (valid && has_bl) ? s.blend[idx] : 1.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float g = 0.0f;
+        if (valid && ch.ok[q]) g = __ldg(ch.gp[q] + t * ch.gst[q] + (long long)i * ch.gsh[q] + j);
+        g_n[q] = has_bl ? __fmul_rn(g, bl) : g;
+      }
+    };
+    if (nb > 0) load(0);
+    for (int b = 0; b < nb; ++b) {
+      const uint4 r = r_n;
+      const float g0 = g_n[0], g1 = g_n[1], g2 = g_n[2], g3 = g_n[3];
+      if (b + 1 < nb) load(b + 1);  // software prefetch of the next batch's gOut
+      const float tx = __uint_as_float(r.x), ty = __uint_as_float(r.y);
+      const float ux = 1.0f - tx, uy = 1.0f - ty;
+      const float w0 = ux * uy, w1 = tx * uy, w2 = ux * ty, w3 = tx * ty;
+      const int px = (int)(r.z & 63u) - 1, py = (int)((r.z >> 6) & 63u) - 1;
+      const unsigned bits = (r.z >> 12) & 15u;
+      const int rank = (int)(r.z >> 16);
+      const int pos = py * OT_W + px;
+      const int mr = s.bmax[b];
+      for (int rr = 0; rr <= mr; ++rr) {
+        const bool on = rank == rr;
+#define FWB_RMW(BIT, OFF, WGT)                                   \
+  if (on && (bits & BIT)) {                                      \
+    float4 a = acc[pos + (OFF)];                                 \
+    a.x = fmaf(WGT, g0, a.x);                                    \
+    a.y = fmaf(WGT, g1, a.y);                                    \
+    a.z = fmaf(WGT, g2, a.z);                                    \
+    a.w = fmaf(WGT, g3, a.w);                                    \
+    acc[pos + (OFF)] = a;                                        \
+  }                                                              \
+  __syncwarp();
+        FWB_RMW(1u, 0, w0)
+        FWB_RMW(2u, 1, w1)
+        FWB_RMW(4u, OT_W, w2)
+        FWB_RMW(8u, OT_W + 1, w3)
+#undef FWB_RMW
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bwd_src_owner_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+                                                            const WsView ws, const __grid_constant__ OwnArgs A) {
+  extern __shared__ float4 smem4[];
   const Geo& G = P.geo;
-  int* s_acc = smem;                                  // [ctot][OT_WORDS]
-  int* s_cnt = s_acc + A.ctot * OT_WORDS;             // [OT_WORDS]
-  float* s_scale = (float*)(s_cnt + OT_WORDS);        // [ctot]
-  float* s_inv = s_scale + A.ctot;                    // [ctot]
-  int* s_hits = (int*)(s_inv + A.ctot);               // [HITCAP]
-  int* s_misc = s_hits + HITCAP;                      // [0] nhit, [1] max fan-in
+  OwnSmem s;
+  s.acc = smem4;
+  s.rec = (uint4*)(s.acc + A.ngrp * OT_PIX);
+  s.blend = (float*)(s.rec + OWN_RC);
+  s.hits = (int*)(s.blend + OWN_RC);
+  s.hits2 = s.hits + OWN_HITCAP;
+  s.bmax = s.hits2 + OWN_HITCAP;
+  s.wcnt = s.bmax + (OWN_RC / 32);
+  s.misc = s.wcnt + 32;
 
   const int d = A.d;
   const int sx0 = blockIdx.x * OT_W, sy0 = blockIdx.y * OT_H;
   const int n = A.tshared ? blockIdx.z : blockIdx.z / G.T;
   const int t_lo = A.tshared ? 0 : blockIdx.z - n * G.T, t_hi = A.tshared ? G.T : t_lo + 1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = OWN_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+  const bool has_bl = P.dir[d].blend != nullptr;
 
-  // The accumulators are 32-bit fixed point with `headroom` integer bits for the fan-in.  If a tile turns out
-  // to receive more than 2^headroom contributions in one pixel (possible overflow), redo it with more headroom.
-  for (int headroom = HEADROOM0;; headroom += 8) {
-    for (int k = tid; k < A.ctot * OT_WORDS + OT_WORDS; k += OWN_THREADS) smem[k] = 0;
-    if (tid == 0) s_misc[1] = 0;
-    // one power-of-two scale per channel from max|gOut*blend| over the frames this tile accumulates
-    if (tid < A.ctot) {
-      int cc = tid, s = 0;
-      while (cc >= A.seg[s].c1 - A.seg[s].c0) {
-        cc -= A.seg[s].c1 - A.seg[s].c0;
-        ++s;
+  // channels of this warp (phase 2 / final store)
+  OwnChan ch;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int cc = warp * 4 + q;
+    ch.ok[q] = warp < A.ngrp && cc < A.nchan;
+    ch.gp[q] = nullptr;
+    ch.op[q] = nullptr;
+    ch.gst[q] = 0;
+    ch.gsh[q] = ch.osh[q] = 0;
+    if (ch.ok[q]) {
+      int sg = 0;
+      while (cc >= A.seg[sg].c1 - A.seg[sg].c0) {
+        cc -= A.seg[sg].c1 - A.seg[sg].c0;
+        ++sg;
       }
-      const int cg = A.seg[s].cbase + cc;
-      unsigned gb = 0u;
-      for (int t = t_lo; t < t_hi; ++t) gb = max(gb, ws.gmax[((size_t)d * ws.NT + n * G.T + t) * ws.ctot + cg]);
-      float sc = 0.0f, inv = 0.0f;
-      if (gb != 0u && gb < 0x7f800000u) {
-        const int E = (int)(gb >> 23) - 127;  // |g| < 2^(E+1)
-        const int e = max(-120, min(120, 30 - (E + 1) - headroom));
-        sc = __uint_as_float((unsigned)(e + 127) << 23);
-        inv = __uint_as_float((unsigned)(-e + 127) << 23);
-      }
-      s_scale[tid] = sc;
-      s_inv[tid] = inv;
+      const int g = A.seg[sg].g, c = A.seg[sg].c0 + cc;
+      ch.gp[q] = Q.grad_out[g] + n * Q.go_sn[g] + (long long)c * Q.go_sc[g];
+      ch.gst[q] = Q.go_st[g];
+      ch.gsh[q] = Q.go_sh[g];
+      ch.op[q] = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + (A.tshared ? 0 : t_lo * Q.gs_st[g][d]) + (long long)c * Q.gs_sc[g][d];
+      ch.osh[q] = Q.gs_sh[g][d];
     }
-    __syncthreads();
+  }
 
-    for (int t = t_lo; t < t_hi; ++t) {
-      const int nt = n * G.T + t;
-      const WsHeader hd = ws.hdr[(size_t)d * ws.NT + nt];
-      // ---- micro-tile records whose displacement window can reach this tile
-      if (hd.dxmin <= hd.dxmax) {
-        // candidate (i,j) with tap column x0 or x0+1 in [sx0, sx0+OT_W): j = x0 - dx, dx in [dxmin-R, dxmax+R]
-        const int jlo = sx0 - 1 - (hd.dxmax + OUTLIER_R), jhi = sx0 + OT_W - 1 - (hd.dxmin - OUTLIER_R);
-        const int ilo = sy0 - 1 - (hd.dymax + OUTLIER_R), ihi = sy0 + OT_H - 1 - (hd.dymin - OUTLIER_R);
-        const int mx0 = max(jlo, 0) / MT_W, mx1 = min(jhi, G.W - 1) / MT_W;
-        const int my0 = max(ilo, 0) / MT_H, my1 = min(ihi, G.H - 1) / MT_H;
-        const int ww = mx1 - mx0 + 1, wh = my1 - my0 + 1;
-        const int total = (jhi < 0 || ihi < 0 || ww <= 0 || wh <= 0) ? 0 : ww * wh;
-        const short4* tab = ws.tab + ((size_t)d * ws.NT + nt) * ws.mth * ws.mtw;
-        for (int base = 0; base < total; base += HITCAP) {
-          if (tid == 0) s_misc[0] = 0;
-          __syncthreads();
-          for (int q = base + tid; q < min(base + HITCAP, total); q += OWN_THREADS) {
-            const int my = my0 + q / ww, mx = mx0 + q % ww;
-            const short4 r = tab[(size_t)my * ws.mtw + mx];
-            if (r.x <= r.y && r.x < sx0 + OT_W && r.y >= sx0 && r.z < sy0 + OT_H && r.w >= sy0)
-              s_hits[atomicAdd(&s_misc[0], 1)] = (my << 16) | mx;
-          }
-          __syncthreads();
-          const int nhit = s_misc[0];
-          for (int h = warp; h < nhit; h += NW) {
-            const int my = s_hits[h] >> 16, mx = s_hits[h] & 0xffff;
-            const int j = mx * MT_W + (lane & 7), i = my * MT_H + (lane >> 3);
-            const bool active = j < G.W && i < G.H;
-            Tap k;
-            k.valid = 0u;
-            k.x0 = k.y0 = 0;
-            if (active) compute_tap(G, P.dir[d], n, t, i, j, k);
-            int adx, ady;
-            unsigned hm;
-            const bool inl = mt_classify(active && k.valid != 0u, k.x0 - j, k.y0 - i, adx, ady, hm);
-            own_pixel(P, Q, A, n, t, i, j, inl, k, sx0, sy0, s_acc, s_cnt, s_scale);
-          }
-          __syncthreads();
-        }
-      }
-      // ---- outlier pixels of this image/direction
-      const int nout = hd.n_outliers;
-      const int2* ol = ws.outl + ((size_t)d * ws.NT + nt) * ws.cap;
-      for (int base = 0; base < nout; base += HITCAP) {
-        if (tid == 0) s_misc[0] = 0;
+  for (int k = tid; k < A.ngrp * OT_PIX; k += nthr) s.acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int nt = n * G.T + t;
+    const WsHeader hd = ws.hdr[(size_t)d * ws.NT + nt];
+    int nrec = 0;
+    // ---- micro-tile records whose displacement window can reach this tile
+    if (hd.dxmin <= hd.dxmax) {
+      // candidate (i,j) with tap column x0 or x0+1 in [sx0, sx0+OT_W): j = x0 - dx, dx in [dxmin-R, dxmax+R]
+      const int jlo = sx0 - 1 - (hd.dxmax + OUTLIER_R), jhi = sx0 + OT_W - 1 - (hd.dxmin - OUTLIER_R);
+      const int ilo = sy0 - 1 - (hd.dymax + OUTLIER_R), ihi = sy0 + OT_H - 1 - (hd.dymin - OUTLIER_R);
+      const int mx0 = max(jlo, 0) / MT_W, mx1 = min(jhi, G.W - 1) / MT_W;
+      const int my0 = max(ilo, 0) / MT_H, my1 = min(ihi, G.H - 1) / MT_H;
+      const int ww = mx1 - mx0 + 1, wh = my1 - my0 + 1;
+      const int total = (jhi < 0 || ihi < 0 || ww <= 0 || wh <= 0) ? 0 : ww * wh;
+      const short4* tab = ws.tab + ((size_t)d * ws.NT + nt) * ws.mth * ws.mtw;
+      for (int base = 0; base < total; base += OWN_HITCAP) {
+        if (tid == 0) s.misc[0] = 0;
         __syncthreads();
-        for (int q = base + tid; q < min(base + HITCAP, nout); q += OWN_THREADS) {
-          const int2 e = ol[q];
-          const int y0 = e.y >> 16, x0 = (int)(short)(e.y & 0xffff);
-          if (x0 < sx0 + OT_W && x0 + 1 >= sx0 && y0 < sy0 + OT_H && y0 + 1 >= sy0) s_hits[atomicAdd(&s_misc[0], 1)] = e.x;
+        for (int q = base + tid; q < min(base + OWN_HITCAP, total); q += nthr) {
+          const int my = my0 + q / ww, mx = mx0 + q % ww;
+          const short4 r = tab[(size_t)my * ws.mtw + mx];
+          if (r.x <= r.y && r.x < sx0 + OT_W && r.y >= sx0 && r.z < sy0 + OT_H && r.w >= sy0)
+            s.hits[atomicAdd(&s.misc[0], 1)] = (my << 16) | mx;
         }
         __syncthreads();
-        const int nhit = s_misc[0];
-        for (int h0 = warp * 32; h0 < nhit; h0 += NW * 32) {
-          const int h = h0 + lane;
-          const bool active = h < nhit;
-          int i = 0, j = 0;
+        const int nhit = s.misc[0];
+        own_sort_hits(s, nhit);
+        __syncthreads();
+        for (int h0 = 0; h0 < nhit; h0 += nw) {
+          if (nrec + nw * 32 > OWN_RC) {
+            own_flush(s, nrec, t, A.ngrp, ch, has_bl);
+            nrec = 0;
+          }
+          const int h = h0 + warp;
           Tap k;
           k.valid = 0u;
           k.x0 = k.y0 = 0;
-          if (active) {
-            const int pix = s_hits[h];
-            i = pix / G.W;
-            j = pix - i * G.W;
-            compute_tap(G, P.dir[d], n, t, i, j, k);
+          k.tx = k.ty = 0.f;
+          k.blend = 1.f;
+          int i = 0, j = 0;
+          bool active = false;
+          if (h < nhit) {
+            const int my = s.hits2[h] >> 16, mx = s.hits2[h] & 0xffff;
+            j = mx * MT_W + (lane & 7);
+            i = my * MT_H + (lane >> 3);
+            active = j < G.W && i < G.H;
+            if (active) compute_tap(G, P.dir[d], n, t, i, j, k);
           }
-          own_pixel(P, Q, A, n, t, i, j, active, k, sx0, sy0, s_acc, s_cnt, s_scale);
+          int adx, ady, px, py;
+          unsigned hm;
+          const bool inl = mt_classify(active && k.valid != 0u, k.x0 - j, k.y0 - i, adx, ady, hm);
+          const unsigned bits = own_bits(k, inl, sx0, sy0, px, py);
+          nrec = own_append(s, nrec, bits != 0u, k, px, py, bits, i, j);
         }
-        __syncthreads();
       }
     }
-    // largest fan-in of the tile: did the fixed-point headroom hold?
-    int m = 0;
-    for (int k = tid; k < OT_WORDS; k += OWN_THREADS) m = max(m, s_cnt[k]);
-    m = __reduce_max_sync(0xffffffffu, m);
-    if (lane == 0) atomicMax(&s_misc[1], m);
-    __syncthreads();
-    const int M = s_misc[1];
-    __syncthreads();
-    if (M <= (1 << headroom) || headroom >= 30) break;
+    // ---- outlier pixels of this image/direction, in ascending pixel order (id ranges that fit the hit list)
+    const int nout = hd.n_outliers;
+    const int2* ol = ws.outl + ((size_t)d * ws.NT + nt) * ws.cap;
+    const int HW = G.H * G.W;
+    for (int lo = 0; lo < HW && nout > 0;) {
+      int hi = HW, cnt;
+      for (;;) {
+        if (tid == 0) s.misc[0] = 0;
+        __syncthreads();
+        for (int q = tid; q < nout; q += nthr) {
+          const int2 e = ol[q];
+          const int y0 = e.y >> 16, x0 = (int)(short)(e.y & 0xffff);
+          if (e.x >= lo && e.x < hi && x0 < sx0 + OT_W && x0 + 1 >= sx0 && y0 < sy0 + OT_H && y0 + 1 >= sy0) {
+            const int slot = atomicAdd(&s.misc[0], 1);
+            if (slot < OWN_HITCAP) s.hits[slot] = e.x;
+          }
+        }
+        __syncthreads();
+        cnt = s.misc[0];
+        __syncthreads();
+        if (cnt <= OWN_HITCAP) break;
+        hi = lo + max((hi - lo) >> 1, 1);  // a range of <= OWN_HITCAP ids always fits (ids are distinct)
+      }
+      own_sort_hits(s, cnt);
+      __syncthreads();
+      for (int h0 = 0; h0 < cnt; h0 += nw * 32) {
+        if (nrec + nw * 32 > OWN_RC) {
+          own_flush(s, nrec, t, A.ngrp, ch, has_bl);
+          nrec = 0;
+        }
+        const int h = h0 + warp * 32 + lane;
+        Tap k;
+        k.valid = 0u;
+        k.x0 = k.y0 = 0;
+        k.tx = k.ty = 0.f;
+        k.blend = 1.f;
+        int i = 0, j = 0;
+        const bool active = h < cnt;
+        if (active) {
+          const int pix = s.hits2[h];
+          i = pix / G.W;
+          j = pix - i * G.W;
+          compute_tap(G, P.dir[d], n, t, i, j, k);
+        }
+        int px, py;
+        const unsigned bits = own_bits(k, active, sx0, sy0, px, py);
+        nrec = own_append(s, nrec, bits != 0u, k, px, py, bits, i, j);
+      }
+      lo = hi;
+    }
+    own_flush(s, nrec, t, A.ngrp, ch, has_bl);
   }
 
-  // ---- write the tile once: plain coalesced stores
-  int cc = 0;
-  for (int s = 0; s < A.nseg; ++s) {
-    const int g = A.seg[s].g;
-    float* gsb = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + (A.tshared ? 0 : t_lo * Q.gs_st[g][d]);
-    for (int c = A.seg[s].c0; c < A.seg[s].c1; ++c, ++cc) {
-      const float inv = s_inv[cc];
-      for (int k = tid; k < OT_W * OT_H; k += OWN_THREADS) {
-        const int yy = k / OT_W, xx = k % OT_W;
-        const int y = sy0 + yy, x = sx0 + xx;
-        if (y < G.H && x < G.W)
-          __stcs(gsb + (long long)c * Q.gs_sc[g][d] + (long long)y * Q.gs_sh[g][d] + x,
-                 (float)s_acc[cc * OT_WORDS + yy * OT_PITCH + xx] * inv);
+  // ---- write the tile once: plain coalesced stores, warp w its 4 channel planes
+  if (warp < A.ngrp) {
+    const float4* acc = s.acc + warp * OT_PIX;
+    for (int pos = lane; pos < OT_PIX; pos += 32) {
+      const int y = sy0 + pos / OT_W, x = sx0 + pos % OT_W;
+      if (y < G.H && x < G.W) {
+        const float4 a = acc[pos];
+        if (ch.ok[0]) __stcs(ch.op[0] + (long long)y * ch.osh[0] + x, a.x);
+        if (ch.ok[1]) __stcs(ch.op[1] + (long long)y * ch.osh[1] + x, a.y);
+        if (ch.ok[2]) __stcs(ch.op[2] + (long long)y * ch.osh[2] + x, a.z);
+        if (ch.ok[3]) __stcs(ch.op[3] + (long long)y * ch.osh[3] + x, a.w);
       }
     }
   }
 }
 
-static inline size_t own_smem_bytes(int ctot) {
-  return sizeof(int) * ((size_t)ctot * OT_WORDS + OT_WORDS + 2 * (size_t)ctot + HITCAP + 8);
+static inline size_t own_smem_bytes(int ngrp) {
+  return sizeof(float4) * (size_t)ngrp * OT_PIX + sizeof(uint4) * OWN_RC + sizeof(float) * OWN_RC +
+         sizeof(int) * (2 * OWN_HITCAP + OWN_RC / 32 + 32 + 8);
 }
 
 }  // namespace fwb
