@@ -8,10 +8,14 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/flowwarp_b200.h"
 #include "fwb_coords.cuh"
+#include "fwb_generic.cuh"
 #include "fwb_owner.cuh"
+#include "fwb_stage.cuh"
+#include "fwb_csr.cuh"
 
 namespace fwb {
 
@@ -29,22 +33,8 @@ __device__ __forceinline__ void thread_pixel(int& i, int& j) {
   i = blockIdx.y * BY + (warp >> 2) * MT_H + (lane >> 3);
 }
 
-__device__ __forceinline__ float ldg_if(const float* p, bool ok) { return ok ? __ldg(p) : 0.0f; }
-
-// 4-tap bilinear value; accumulation order nw, ne, sw, se (torch:_decomp/decompositions.py:4515-4537)
-__device__ __forceinline__ float bilinear(const float* __restrict__ s, int o, int sh, unsigned v, float wnw,
-                                          float wne, float wsw, float wse) {
-  const float a = ldg_if(s + o, v & 1u), b = ldg_if(s + o + 1, v & 2u);
-  const float c = ldg_if(s + o + sh, v & 4u), d = ldg_if(s + o + sh + 1, v & 8u);
-  float r = __fmul_rn(a, wnw);
-  r = __fmaf_rn(b, wne, r);
-  r = __fmaf_rn(c, wsw, r);
-  r = __fmaf_rn(d, wse, r);
-  return r;
-}
-
 // ---------------------------------------------------------------------------------------------
-// Kernel 1: fused forward warp (+gate) (+blend) for NDIRS directions and all channel groups.
+// Kernel 1 (generic): one thread per pixel, gather from global memory (fwb_generic.cuh).
 // ---------------------------------------------------------------------------------------------
 template <int NDIRS>
 __global__ void __launch_bounds__(NTHREADS) fwd_kernel(const __grid_constant__ Params P) {
@@ -53,48 +43,7 @@ __global__ void __launch_bounds__(NTHREADS) fwd_kernel(const __grid_constant__ P
   thread_pixel(i, j);
   if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
-
-  float w[NDIRS][4], bl[NDIRS];
-  int x0[NDIRS], y0[NDIRS];
-  unsigned v[NDIRS];
-  bool has_bl[NDIRS];
-#pragma unroll
-  for (int d = 0; d < NDIRS; ++d) {
-    Tap k;
-    compute_tap(G, P.dir[d], n, t, i, j, k);
-    w[d][0] = __fmul_rn(k.ux, k.uy);
-    w[d][1] = __fmul_rn(k.tx, k.uy);
-    w[d][2] = __fmul_rn(k.ux, k.ty);
-    w[d][3] = __fmul_rn(k.tx, k.ty);
-    x0[d] = k.x0;
-    y0[d] = k.y0;
-    v[d] = k.valid;
-    bl[d] = k.blend;
-    has_bl[d] = P.dir[d].blend != nullptr;
-  }
-  for (int g = 0; g < G.n_groups; ++g) {
-    const GroupP& R = P.grp[g];
-    const float* s[NDIRS];
-    int o[NDIRS];
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
-      o[d] = y0[d] * R.src_sh[d] + x0[d];
-    }
-    float* out = R.out + n * R.out_sn + t * R.out_st + (long long)i * R.out_sh + j;
-#pragma unroll 4
-    for (int c = 0; c < R.C; ++c) {
-      float r = 0.0f;
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        float a = bilinear(s[d] + (long long)c * R.src_sc[d], o[d], R.src_sh[d], v[d], w[d][0], w[d][1],
-                           w[d][2], w[d][3]);
-        if (has_bl[d]) a = __fmul_rn(a, bl[d]);
-        r = (d == 0) ? a : __fadd_rn(r, a);
-      }
-      __stcs(out + (long long)c * R.out_sc, r);
-    }
-  }
+  fwd_generic_pixel<NDIRS>(P, n, t, i, j);
 }
 
 // Debug / parity kernel: integer indices, validity bits, float coordinates of one direction.
@@ -117,10 +66,7 @@ __global__ void indices_kernel(const __grid_constant__ Params P, int d, int* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel 2: gradient w.r.t. flow / gate / blend weight — a pure gather, one thread per pixel.
-//   gix = sum_c gw_c * [ uy*(v_ne - v_nw) + ty*(v_se - v_sw) ]
-//   giy = sum_c gw_c * [ ux*(v_sw - v_nw) + tx*(v_se - v_ne) ]       (OOB tap value = 0)
-// which is ATen's grid_sampler_2d_backward accumulation with the common factors pulled out.
+// Kernel 2 (generic): gradient w.r.t. flow / gate / blend weight — a pure gather, one thread per pixel.
 // ---------------------------------------------------------------------------------------------
 template <int NDIRS>
 __global__ void __launch_bounds__(NTHREADS) bwd_flow_kernel(const __grid_constant__ Params P,
@@ -130,67 +76,7 @@ __global__ void __launch_bounds__(NTHREADS) bwd_flow_kernel(const __grid_constan
   thread_pixel(i, j);
   if (j >= G.W || i >= G.H) return;
   const int n = blockIdx.z / G.T, t = blockIdx.z - n * G.T;
-
-  Tap k[NDIRS];
-  float gix[NDIRS], giy[NDIRS], gbl[NDIRS];
-  bool has_bl[NDIRS];
-#pragma unroll
-  for (int d = 0; d < NDIRS; ++d) {
-    compute_tap(G, P.dir[d], n, t, i, j, k[d]);
-    gix[d] = giy[d] = gbl[d] = 0.0f;
-    has_bl[d] = P.dir[d].blend != nullptr;
-  }
-  for (int g = 0; g < G.n_groups; ++g) {
-    const GroupP& R = P.grp[g];
-    if (!Q.grad_out[g]) continue;
-    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
-    const float* s[NDIRS];
-    int o[NDIRS];
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      s[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d];
-      o[d] = k[d].y0 * R.src_sh[d] + k[d].x0;
-    }
-#pragma unroll 2
-    for (int c = 0; c < R.C; ++c) {
-      const float gout = __ldg(go + (long long)c * Q.go_sc[g]);
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        const float* sp = s[d] + (long long)c * R.src_sc[d] + o[d];
-        const int sh = R.src_sh[d];
-        const unsigned v = k[d].valid;
-        const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
-        const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
-        float gw = gout;
-        if (has_bl[d]) {
-          const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
-          gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
-          gw = gout * k[d].blend;
-        }
-        gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
-        giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
-      }
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < NDIRS; ++d) {
-    float gfx = k[d].mx * gix[d], gfy = k[d].my * giy[d];
-    if (P.dir[d].sign < 0.0f) {
-      gfx = -gfx;
-      gfy = -gfy;
-    }
-    const bool gated = P.dir[d].gate != nullptr;
-    if (Q.grad_gate[d] && gated)
-      Q.grad_gate[d][n * Q.gg_sn[d] + t * Q.gg_st[d] + (long long)i * Q.gg_sh[d] + j] =
-          __fadd_rn(__fmul_rn(gfx, k[d].fx), __fmul_rn(gfy, k[d].fy));
-    if (Q.grad_flow[d]) {
-      float* o = Q.grad_flow[d] + n * Q.gf_sn[d] + t * Q.gf_st[d] + (long long)i * Q.gf_sh[d] + j;
-      o[0] = gated ? gfx * k[d].gate : gfx;
-      o[Q.gf_sc[d]] = gated ? gfy * k[d].gate : gfy;
-    }
-    if (Q.grad_blend[d] && has_bl[d])
-      Q.grad_blend[d][n * Q.gb_sn[d] + t * Q.gb_st[d] + (long long)i * Q.gb_sh[d] + j] = gbl[d];
-  }
+  bwdflow_generic_pixel<NDIRS>(P, Q, n, t, i, j);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -383,6 +269,44 @@ static dim3 pixel_grid(const fwb_problem* p) {
   return dim3((p->W + BX - 1) / BX, (p->H + BY - 1) / BY, p->N * p->T);
 }
 
+static dim3 stage_grid(const fwb_problem* p) {
+  return dim3((p->W + ST_TW - 1) / ST_TW, (p->H + ST_TH - 1) / ST_TH, p->N * p->T);
+}
+
+// development knobs (read once): FWB_GENERIC=1 forces the global-gather kernels, FWB_SMEM_KB sets the dynamic
+// shared memory of the staged kernels (default 104 KB -> 2 CTAs per SM)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+static int stage_smem_bytes() {
+  static const int kb = env_int("FWB_SMEM_KB", 104);
+  return kb * 1024;
+}
+static bool force_generic() {
+  static const int g = env_int("FWB_GENERIC", 0);
+  return g != 0;
+}
+
+// the staged kernels move 16-byte pieces of the source planes with cp.async: every source pointer must be
+// 16-byte aligned and every stride a multiple of 4 elements
+static bool stage_ok(const fwb_problem* p) {
+  if (force_generic()) return false;
+  for (int g = 0; g < p->n_groups; ++g)
+    for (int d = 0; d < p->n_dirs; ++d) {
+      const fwb_group* R = &p->grp[g];
+      if (((uintptr_t)R->src[d] & 15u) || (R->src_sn[d] & 3) || (R->src_st[d] & 3) || (R->src_sc[d] & 3) ||
+          (R->src_sh[d] & 3))
+        return false;
+    }
+  return true;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 }  // namespace fwb
 
 using namespace fwb;
@@ -418,6 +342,17 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   Params P;
   to_params(p, P);
   cudaStream_t s = (cudaStream_t)stream;
+  if (stage_ok(p)) {
+    const int sb = stage_smem_bytes();
+    if (p->n_dirs == 2) {
+      if ((rc = set_smem(fwd_staged_kernel<2>, sb))) return rc;
+      fwd_staged_kernel<2><<<stage_grid(p), ST_THREADS, sb, s>>>(P, sb / 4);
+    } else {
+      if ((rc = set_smem(fwd_staged_kernel<1>, sb))) return rc;
+      fwd_staged_kernel<1><<<stage_grid(p), ST_THREADS, sb, s>>>(P, sb / 4);
+    }
+    return (int32_t)cudaGetLastError();
+  }
   const dim3 grid = pixel_grid(p), block(NTHREADS);
   if (p->n_dirs == 2)
     fwd_kernel<2><<<grid, block, 0, s>>>(P);
@@ -470,7 +405,16 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   }
   int want = 0;
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
-  if (want) {
+  if (want && stage_ok(p)) {
+    const int sb = stage_smem_bytes();
+    if (p->n_dirs == 2) {
+      if ((rc = set_smem(bwd_flow_staged_kernel<2>, sb))) return rc;
+      bwd_flow_staged_kernel<2><<<stage_grid(p), ST_THREADS, sb, s>>>(P, Q, sb / 4);
+    } else {
+      if ((rc = set_smem(bwd_flow_staged_kernel<1>, sb))) return rc;
+      bwd_flow_staged_kernel<1><<<stage_grid(p), ST_THREADS, sb, s>>>(P, Q, sb / 4);
+    }
+  } else if (want) {
     const dim3 grid = pixel_grid(p), block(NTHREADS);
     if (p->n_dirs == 2)
       bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
@@ -497,6 +441,33 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
     const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
     if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
     const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
+    if (env_int("FWB_OWNER", 0) == 0) {
+      // ---- owner gather over contributor lists (fwb_csr.cuh)
+      const int dyn = env_int("FWB_CSR_KB", 110) * 1024;
+      if ((size_t)dyn < csr_smem_bytes(0)) return FWB_E_WORKSPACE;
+      if ((rc = set_smem(bwd_src_csr_kernel, dyn))) return rc;
+      for (int d = 0; d < p->n_dirs; ++d)
+        for (int shared = 0; shared < 2; ++shared) {
+          CsrArgs A = {};
+          A.d = d;
+          A.tshared = shared;
+          A.gout_vec = force_generic() ? 0 : 1;
+          A.stage_floats = (int)((dyn - csr_fixed_bytes()) / 4);
+          for (int gi = 0; gi < p->n_groups; ++gi) {
+            if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
+            const int is_shared = (Q.gs_st[gi][d] == 0 && p->T > 1) ? 1 : 0;
+            if (is_shared != shared) continue;
+            A.group_mask |= 1u << gi;
+            if (((uintptr_t)Q.grad_out[gi] & 15u) || (Q.go_sn[gi] & 3) || (Q.go_st[gi] & 3) || (Q.go_sc[gi] & 3) ||
+                (Q.go_sh[gi] & 3))
+              A.gout_vec = 0;
+          }
+          if (!A.group_mask) continue;
+          const dim3 grid((p->W + CS_TW - 1) / CS_TW, (p->H + CS_TH - 1) / CS_TH, shared ? p->N : NT);
+          bwd_src_csr_kernel<<<grid, CS_THREADS, dyn, s>>>(P, Q, ws, A);
+          if ((rc = (int32_t)cudaGetLastError())) return rc;
+        }
+    } else {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(bwd_src_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -540,6 +511,7 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
         }
         if ((rc = flush())) return rc;
       }
+    }
     // a group whose grad_out is NULL contributes nothing: its grad_src is zero
     for (int gi = 0; gi < p->n_groups; ++gi)
       for (int d = 0; d < p->n_dirs; ++d)
