@@ -15,6 +15,7 @@
 #include "fwb_generic.cuh"
 #include "fwb_owner.cuh"
 #include "fwb_stage.cuh"
+#include "fwb_pair.cuh"
 #include "fwb_csr.cuh"
 
 namespace fwb {
@@ -270,7 +271,7 @@ static dim3 pixel_grid(const fwb_problem* p) {
 }
 
 static dim3 stage_grid(const fwb_problem* p) {
-  return dim3((p->W + ST_TW - 1) / ST_TW, (p->H + ST_TH - 1) / ST_TH, p->N * p->T);
+  return dim3((p->W + PR_TW - 1) / PR_TW, (p->H + PR_TH - 1) / PR_TH, p->N * p->T);
 }
 
 // development knobs (read once): FWB_GENERIC=1 forces the global-gather kernels, FWB_SMEM_KB sets the dynamic
@@ -280,7 +281,7 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 static int stage_smem_bytes() {
-  static const int kb = env_int("FWB_SMEM_KB", 104);
+  static const int kb = env_int("FWB_SMEM_KB", 62);
   return kb * 1024;
 }
 static bool force_generic() {
@@ -291,7 +292,7 @@ static bool force_generic() {
 // the staged kernels move 16-byte pieces of the source planes with cp.async: every source pointer must be
 // 16-byte aligned and every stride a multiple of 4 elements
 static bool stage_ok(const fwb_problem* p) {
-  if (force_generic()) return false;
+  if (force_generic() || (p->W & 3)) return false;  // a 16-byte piece is all inside or all outside the image
   for (int g = 0; g < p->n_groups; ++g)
     for (int d = 0; d < p->n_dirs; ++d) {
       const fwb_group* R = &p->grp[g];
@@ -344,13 +345,23 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (stage_ok(p)) {
     const int sb = stage_smem_bytes();
-    if (p->n_dirs == 2) {
-      if ((rc = set_smem(fwd_staged_kernel<2>, sb))) return rc;
-      fwd_staged_kernel<2><<<stage_grid(p), ST_THREADS, sb, s>>>(P, sb / 4);
-    } else {
-      if ((rc = set_smem(fwd_staged_kernel<1>, sb))) return rc;
-      fwd_staged_kernel<1><<<stage_grid(p), ST_THREADS, sb, s>>>(P, sb / 4);
+#define FWB_LAUNCH_FWD(D, A, B)                                                      \
+  do {                                                                               \
+    if ((rc = set_smem(fwd_pair_kernel<D, A, B>, sb))) return rc;                    \
+    fwd_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, sb / 4);       \
+  } while (0)
+    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+    switch (key) {
+      case 0: FWB_LAUNCH_FWD(1, false, false); break;
+      case 1: FWB_LAUNCH_FWD(1, false, true); break;
+      case 2: FWB_LAUNCH_FWD(1, true, false); break;
+      case 3: FWB_LAUNCH_FWD(1, true, true); break;
+      case 4: FWB_LAUNCH_FWD(2, false, false); break;
+      case 5: FWB_LAUNCH_FWD(2, false, true); break;
+      case 6: FWB_LAUNCH_FWD(2, true, false); break;
+      default: FWB_LAUNCH_FWD(2, true, true); break;
     }
+#undef FWB_LAUNCH_FWD
     return (int32_t)cudaGetLastError();
   }
   const dim3 grid = pixel_grid(p), block(NTHREADS);
@@ -407,13 +418,23 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
   if (want && stage_ok(p)) {
     const int sb = stage_smem_bytes();
-    if (p->n_dirs == 2) {
-      if ((rc = set_smem(bwd_flow_staged_kernel<2>, sb))) return rc;
-      bwd_flow_staged_kernel<2><<<stage_grid(p), ST_THREADS, sb, s>>>(P, Q, sb / 4);
-    } else {
-      if ((rc = set_smem(bwd_flow_staged_kernel<1>, sb))) return rc;
-      bwd_flow_staged_kernel<1><<<stage_grid(p), ST_THREADS, sb, s>>>(P, Q, sb / 4);
+#define FWB_LAUNCH_BWF(D, A, B)                                                         \
+  do {                                                                                  \
+    if ((rc = set_smem(bwd_flow_pair_kernel<D, A, B>, sb))) return rc;                  \
+    bwd_flow_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
+  } while (0)
+    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+    switch (key) {
+      case 0: FWB_LAUNCH_BWF(1, false, false); break;
+      case 1: FWB_LAUNCH_BWF(1, false, true); break;
+      case 2: FWB_LAUNCH_BWF(1, true, false); break;
+      case 3: FWB_LAUNCH_BWF(1, true, true); break;
+      case 4: FWB_LAUNCH_BWF(2, false, false); break;
+      case 5: FWB_LAUNCH_BWF(2, false, true); break;
+      case 6: FWB_LAUNCH_BWF(2, true, false); break;
+      default: FWB_LAUNCH_BWF(2, true, true); break;
     }
+#undef FWB_LAUNCH_BWF
   } else if (want) {
     const dim3 grid = pixel_grid(p), block(NTHREADS);
     if (p->n_dirs == 2)
@@ -453,6 +474,7 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
           A.tshared = shared;
           A.gout_vec = force_generic() ? 0 : 1;
           A.stage_floats = (int)((dyn - csr_fixed_bytes()) / 4);
+          A.long_len = min(31, max(2, env_int("FWB_CSR_LONG", 28)));
           for (int gi = 0; gi < p->n_groups; ++gi) {
             if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
             const int is_shared = (Q.gs_st[gi][d] == 0 && p->T > 1) ? 1 : 0;

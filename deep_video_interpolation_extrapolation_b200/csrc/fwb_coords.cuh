@@ -83,19 +83,33 @@ struct Tap {
   float fx, fy, gate, blend;
 };
 
+// The direction's tensors at one (n, t): hoists the 64-bit batch/frame offsets out of the per-pixel code.
+struct DirAt {
+  const float* flow;
+  const float* gate;   // nullptr: no gate
+  const float* blend;  // nullptr: no blend weight
+};
+__device__ __forceinline__ DirAt dir_at(const DirP& D, int n, int t) {
+  DirAt a;
+  a.flow = D.flow + n * D.flow_sn + t * D.flow_st;
+  a.gate = D.gate ? D.gate + n * D.gate_sn + t * D.gate_st : nullptr;
+  a.blend = D.blend ? D.blend + n * D.blend_sn + t * D.blend_st : nullptr;
+  return a;
+}
+
 // Everything channel-independent about one (pixel, direction).
-__device__ __forceinline__ void compute_tap(const Geo& G, const DirP& D, int n, int t, int i, int j, Tap& k) {
-  const long long fo = n * D.flow_sn + t * D.flow_st + (long long)i * D.flow_sh + j;
-  float fx = __ldg(D.flow + fo), fy = __ldg(D.flow + fo + D.flow_sc);
+__device__ __forceinline__ void compute_tap_at(const Geo& G, const DirP& D, const DirAt& A, int i, int j, Tap& k) {
+  const float* fp = A.flow + (long long)i * D.flow_sh + j;
+  float fx = __ldg(fp), fy = __ldg(fp + D.flow_sc);
   k.fx = fx;
   k.fy = fy;
   k.gate = 1.0f;
-  if (D.gate) {
-    k.gate = __ldg(D.gate + n * D.gate_sn + t * D.gate_st + (long long)i * D.gate_sh + j);
+  if (A.gate) {
+    k.gate = __ldg(A.gate + (long long)i * D.gate_sh + j);
     fx = __fmul_rn(fx, k.gate);
     fy = __fmul_rn(fy, k.gate);
   }
-  k.blend = D.blend ? __ldg(D.blend + n * D.blend_sn + t * D.blend_st + (long long)i * D.blend_sh + j) : 1.0f;
+  k.blend = A.blend ? __ldg(A.blend + (long long)i * D.blend_sh + j) : 1.0f;
   const float bx = base_coord(j, G.W, G.stepx), by = base_coord(i, G.H, G.stepy);
   const float gx = D.sign < 0.0f ? __fsub_rn(bx, fx) : __fadd_rn(bx, fx);
   const float gy = D.sign < 0.0f ? __fsub_rn(by, fy) : __fadd_rn(by, fy);
@@ -108,6 +122,61 @@ __device__ __forceinline__ void compute_tap(const Geo& G, const DirP& D, int n, 
   k.ty = __fsub_rn(k.iy, fy0);
   k.ux = __fsub_rn(__fadd_rn(fx0, 1.0f), k.ix);
   k.uy = __fsub_rn(__fadd_rn(fy0, 1.0f), k.iy);
+  const bool xin0 = (unsigned)k.x0 < (unsigned)G.W, xin1 = (unsigned)(k.x0 + 1) < (unsigned)G.W;
+  const bool yin0 = (unsigned)k.y0 < (unsigned)G.H, yin1 = (unsigned)(k.y0 + 1) < (unsigned)G.H;
+  k.valid = (unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
+            ((unsigned)(xin1 && yin1) << 3);
+}
+
+__device__ __forceinline__ void compute_tap(const Geo& G, const DirP& D, int n, int t, int i, int j, Tap& k) {
+  compute_tap_at(G, D, dir_at(D, n, t), i, j, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same arithmetic with the padding / align mode as template parameters and only the outputs the staged
+// kernels need (no gradient multipliers, no raw flow): roughly a third of the instructions.  Bit-identical to
+// compute_tap for x0, y0, valid, tx, ty, ux, uy, blend (every rounding is the same operation in the same order).
+// ---------------------------------------------------------------------------------------------
+struct FastTap {
+  int x0, y0;
+  unsigned valid;
+  float tx, ty, ux, uy, blend;
+};
+
+template <bool ALIGN, bool BORDER>
+__device__ __forceinline__ float source_index_fast(float g, float fs, float fs1) {
+  float c = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), fs1) : __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.0f), fs, -1.0f), 0.5f);
+  if (BORDER) {
+    c = fminf(fmaxf(c, 0.0f), fs1);  // NaN -> 0 (fmaxf), <= 0 -> 0, >= size-1 -> size-1: source_index's clip
+  } else {
+    c = (c <= 2147483648.0f && c >= -2147483648.0f) ? c : -100.0f;  // non-finite / beyond int: far outside
+  }
+  return c;
+}
+
+// bx = base_coord(j, W, stepx) is the same for every pixel of a thread (lane = column): passed in.
+template <bool ALIGN, bool BORDER>
+__device__ __forceinline__ void compute_tap_fast(const Geo& G, const DirP& D, const DirAt& A, float bx, int i, int j, FastTap& k) {
+  const float* fp = A.flow + (long long)i * D.flow_sh + j;
+  float fx = __ldg(fp), fy = __ldg(fp + D.flow_sc);
+  if (A.gate) {
+    const float gate = __ldg(A.gate + (long long)i * D.gate_sh + j);
+    fx = __fmul_rn(fx, gate);
+    fy = __fmul_rn(fy, gate);
+  }
+  k.blend = A.blend ? __ldg(A.blend + (long long)i * D.blend_sh + j) : 1.0f;
+  const float by = base_coord(i, G.H, G.stepy);
+  // bx -/+ f as one fma: sign * f is exact, so this is the same single rounding as __fsub_rn / __fadd_rn
+  const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by);
+  const float ix = source_index_fast<ALIGN, BORDER>(gx, (float)G.W, (float)(G.W - 1));
+  const float iy = source_index_fast<ALIGN, BORDER>(gy, (float)G.H, (float)(G.H - 1));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  k.x0 = (int)fx0;
+  k.y0 = (int)fy0;
+  k.tx = __fsub_rn(ix, fx0);
+  k.ty = __fsub_rn(iy, fy0);
+  k.ux = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+  k.uy = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
   const bool xin0 = (unsigned)k.x0 < (unsigned)G.W, xin1 = (unsigned)(k.x0 + 1) < (unsigned)G.W;
   const bool yin0 = (unsigned)k.y0 < (unsigned)G.H, yin1 = (unsigned)(k.y0 + 1) < (unsigned)G.H;
   k.valid = (unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |

@@ -32,6 +32,7 @@ constexpr int CS_HITCAP = 512;               // micro-tile / outlier hits per sc
 constexpr int CS_MAXOUT = 256;               // far contributors per flush (one staged cell each)
 constexpr int CS_OUTROUND = 64;              // outlier candidates examined per round
 constexpr int CS_CCMAX = 4;                  // grad_out planes per chunk
+constexpr int CS_LONG = 17;                  // a list of this many records or more is walked by a whole warp
 
 struct CsrArgs {
   int d;         // direction
@@ -39,6 +40,7 @@ struct CsrArgs {
   int gout_vec;  // every grad_out pointer is 16-byte aligned with strides % 4 == 0 (cp.async staging allowed)
   unsigned group_mask;  // groups served by this launch
   int stage_floats;     // floats of shared memory available for staging
+  int long_len;         // a list of this many records or more (<= 31) is walked by a whole warp
 };
 
 struct CsrSmem {
@@ -100,6 +102,12 @@ __device__ __forceinline__ CsrSmem csr_carve(float4* base) {
   s.r_ty = s.r_tx + CS_RC;
   s.r_bl = s.r_ty + CS_RC;
   return s;
+}
+
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+  return v;
 }
 
 // sort the `n` distinct values of s.hits into s.hits2 (rank by counting; n <= CS_HITCAP)
@@ -164,8 +172,11 @@ __device__ __forceinline__ void csr_append(const CsrSmem& s, int& nrec, int& nen
 // So it is enough to group the RECORDS by base cell (one entry per record, not four): pixel c then walks the
 // two contiguous ranges  [base c-(1,0), base c]  (taking ne, then nw)  and  [base c-(1,1), base c-(0,1)]  (se, sw).
 // Inside a base cell the records are ordered by record number, which is a fixed order -> bit-exact run to run.
-__device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const CsrArgs& A, const CsrSmem& s, StageTab& gtab,
-                                       int n, int t, int nrec, int nin, bool accumulate) {
+__device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const CsrArgs& A, int n, int t, int nrec, int nin,
+                                       bool accumulate) {
+  extern __shared__ float4 cs_smem4[];  // carved here (not passed in) so that every access compiles to LDS/STS
+  __shared__ StageTab gtab;
+  const CsrSmem s = csr_carve(cs_smem4);
   const Geo& G = P.geo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = A.d;
@@ -241,7 +252,7 @@ __device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const Cs
     const int pos = tid + CS_THREADS * q;
     const int bA = ((pos >> 5) + 1) * CS_BW + (pos & 31) + 1, bB = bA - CS_BW;
     const int len = (s.boff[bA + 1] - s.boff[bA - 1]) + (s.boff[bB + 1] - s.boff[bB - 1]);
-    atomicAdd(&s.bkt[min(len, 31)], 1);
+    atomicAdd(&s.bkt[min(len, A.long_len)], 1);
   }
   __syncthreads();
   // ---- B4: rank every record inside its base cell (by record number) and emit the sorted copy: one thread
@@ -288,29 +299,37 @@ __device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const Cs
     if (tid < nfar) far_ij = (int)s.r_ij[nin + tid];
   }
   __syncthreads();  // records are dead from here on (the staging area overwrites them)
+  const int long_start = s.bkt[A.long_len];  // perm[long_start ..] are the pixels with long lists
+  __syncthreads();
 #pragma unroll
   for (int q = 0; q < CS_PPT; ++q) {
     const int pos = tid + CS_THREADS * q;
     const int bA = ((pos >> 5) + 1) * CS_BW + (pos & 31) + 1, bB = bA - CS_BW;
     const int len = (s.boff[bA + 1] - s.boff[bA - 1]) + (s.boff[bB + 1] - s.boff[bB - 1]);
-    s.perm[atomicAdd(&s.bkt[min(len, 31)], 1)] = (unsigned short)pos;
+    s.perm[atomicAdd(&s.bkt[min(len, A.long_len)], 1)] = (unsigned short)pos;
   }
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(s.stage);
   if (staged)
     for (int k = tid; k < 2 * cc * ST_ZPAD; k += CS_THREADS) s.stage[(k / ST_ZPAD) * plane + (k % ST_ZPAD)] = 0.f;
   __syncthreads();
   // this thread's 4 pixels: the two record ranges and where the tap changes inside each
-  int opos[CS_PPT], r1b[CS_PPT], r1m[CS_PPT], r1e[CS_PPT], r2b[CS_PPT], r2m[CS_PPT], r2e[CS_PPT];
+  // range 1 = [r1b, r1b + len1): ne taps up to r1m, then nw; range 2 starts at r2b: se taps up to r2m, then sw.
+  // Both are walked by ONE loop of `tot` iterations (equal across a warp thanks to B5).
+  int opos[CS_PPT], r1b[CS_PPT], r1m[CS_PPT], len1[CS_PPT], d2[CS_PPT], r2m[CS_PPT], tot[CS_PPT];
 #pragma unroll
   for (int q = 0; q < CS_PPT; ++q) {
-    opos[q] = s.perm[tid + CS_THREADS * q];
+    // ranks are dealt to the warps in alternating direction so that every warp gets a similar total
+    const int rk = CS_THREADS * q + ((q & 1) ? CS_THREADS - 1 - tid : tid);
+    opos[q] = s.perm[rk];
     const int bA = ((opos[q] >> 5) + 1) * CS_BW + (opos[q] & 31) + 1, bB = bA - CS_BW;
     r1b[q] = s.boff[bA - 1];  // base (px-1, py): ne tap
     r1m[q] = s.boff[bA];      // base (px, py):   nw tap
-    r1e[q] = s.boff[bA + 1];
-    r2b[q] = s.boff[bB - 1];  // base (px-1, py-1): se tap
-    r2m[q] = s.boff[bB];      // base (px, py-1):   sw tap
-    r2e[q] = s.boff[bB + 1];
+    len1[q] = s.boff[bA + 1] - r1b[q];
+    const int r2b = s.boff[bB - 1];  // base (px-1, py-1): se tap
+    r2m[q] = s.boff[bB];             // base (px, py-1):   sw tap
+    tot[q] = len1[q] + s.boff[bB + 1] - r2b;
+    d2[q] = r2b - len1[q];
+    if (rk >= long_start) opos[q] = -1;  // served by the warp-cooperative pass below
   }
 
   for (int g = 0; g < G.n_groups; ++g) {
@@ -354,34 +373,36 @@ __device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const Cs
         }
         __syncthreads();
       }
-      // plane base pointers; staged: planes past nch alias plane 0 (finite data, result unused)
-      const char* sp0;
-      long long pstride;
-      if (staged) {
-        sp0 = reinterpret_cast<const char*>(s.stage + stage * cc * plane);
-        pstride = 4 * plane;
-      } else {
-        sp0 = reinterpret_cast<const char*>(gp + (long long)c0 * gsc);
-        pstride = 4ll * gsc;
-      }
-      const char* sp1 = sp0 + pstride * (nch > 1);
-      const char* sp2 = sp0 + 2 * pstride * (nch > 2);
-      const char* sp3 = sp0 + 3 * pstride * (nch > 3);
+      // staged: shared-space byte addresses of the chunk's planes; planes past nch alias plane 0 (finite data,
+      // result unused)
+      const unsigned sp0 = sbase + 4u * (unsigned)(stage * cc * plane);
+      const unsigned sp1 = sp0 + 4u * (unsigned)(plane * (nch > 1));
+      const unsigned sp2 = sp0 + 8u * (unsigned)(plane * (nch > 2));
+      const unsigned sp3 = sp0 + 12u * (unsigned)(plane * (nch > 3));
+      const float* gp0 = gp + (long long)c0 * gsc;
 #pragma unroll
       for (int q = 0; q < CS_PPT; ++q) {
+        if (opos[q] < 0) continue;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int kb = h ? r2b[q] : r1b[q], km = h ? r2m[q] : r1m[q], ke = h ? r2e[q] : r1e[q];
-          for (int k = kb; k < ke; ++k) {
-            const float4 w4 = s.sw[k];
-            const unsigned so = s.so[k];
-            const float w = h ? (k < km ? w4.w : w4.z) : (k < km ? w4.y : w4.x);
-            const long long o = staged ? (long long)so : 4ll * ((long long)(so >> 16) * gsh + (long long)(so & 0xffffu));
-            acc0 = fmaf(w, *reinterpret_cast<const float*>(sp0 + o), acc0);
-            acc1 = fmaf(w, *reinterpret_cast<const float*>(sp1 + o), acc1);
-            acc2 = fmaf(w, *reinterpret_cast<const float*>(sp2 + o), acc2);
-            acc3 = fmaf(w, *reinterpret_cast<const float*>(sp3 + o), acc3);
+        for (int it = 0; it < tot[q]; ++it) {
+          const bool first = it < len1[q];
+          const int k = first ? r1b[q] + it : it + d2[q];
+          const float4 w4 = s.sw[k];
+          const unsigned so = s.so[k];
+          const bool lo = k < (first ? r1m[q] : r2m[q]);
+          const float wa = lo ? w4.y : w4.x, wb = lo ? w4.w : w4.z;
+          const float w = first ? wa : wb;
+          if (staged) {
+            acc0 = fmaf(w, lds_f32(sp0 + so), acc0);
+            acc1 = fmaf(w, lds_f32(sp1 + so), acc1);
+            acc2 = fmaf(w, lds_f32(sp2 + so), acc2);
+            acc3 = fmaf(w, lds_f32(sp3 + so), acc3);
+          } else {
+            const float* cell = gp0 + (int)(so >> 16) * gsh + (int)(so & 0xffffu);
+            acc0 = fmaf(w, __ldg(cell), acc0);
+            if (nch > 1) acc1 = fmaf(w, __ldg(cell + gsc), acc1);
+            if (nch > 2) acc2 = fmaf(w, __ldg(cell + 2ll * gsc), acc2);
+            if (nch > 3) acc3 = fmaf(w, __ldg(cell + 3ll * gsc), acc3);
           }
         }
         const int oy = blockIdx.y * CS_TH + (opos[q] >> 5), ox = blockIdx.x * CS_TW + (opos[q] & 31);
@@ -397,6 +418,49 @@ __device__ __noinline__ void csr_flush(const Params& P, const GradP& Q, const Cs
             }
         }
       }
+      // long lists: one warp per pixel, lane l takes records l, l+32, ...; fixed butterfly order
+      for (int lp = long_start + warp; lp < CS_PIX; lp += CS_THREADS / 32) {
+        const int pos = s.perm[lp];
+        const int bA = ((pos >> 5) + 1) * CS_BW + (pos & 31) + 1, bB = bA - CS_BW;
+        const int a1b = s.boff[bA - 1], a1m = s.boff[bA], l1 = s.boff[bA + 1] - a1b;
+        const int a2b = s.boff[bB - 1], a2m = s.boff[bB], tl = l1 + s.boff[bB + 1] - a2b;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int it = lane; it < tl; it += 32) {
+          const bool first = it < l1;
+          const int k = first ? a1b + it : a2b + it - l1;
+          const float4 w4 = s.sw[k];
+          const unsigned so = s.so[k];
+          const bool lo = k < (first ? a1m : a2m);
+          const float wa = lo ? w4.y : w4.x, wb = lo ? w4.w : w4.z;
+          const float w = first ? wa : wb;
+          if (staged) {
+            acc0 = fmaf(w, lds_f32(sp0 + so), acc0);
+            acc1 = fmaf(w, lds_f32(sp1 + so), acc1);
+            acc2 = fmaf(w, lds_f32(sp2 + so), acc2);
+            acc3 = fmaf(w, lds_f32(sp3 + so), acc3);
+          } else {
+            const float* cell = gp0 + (int)(so >> 16) * gsh + (int)(so & 0xffffu);
+            acc0 = fmaf(w, __ldg(cell), acc0);
+            if (nch > 1) acc1 = fmaf(w, __ldg(cell + gsc), acc1);
+            if (nch > 2) acc2 = fmaf(w, __ldg(cell + 2ll * gsc), acc2);
+            if (nch > 3) acc3 = fmaf(w, __ldg(cell + 3ll * gsc), acc3);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+          acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+          acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+          acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
+        }
+        const int oy = blockIdx.y * CS_TH + (pos >> 5), ox = blockIdx.x * CS_TW + (pos & 31);
+        if (lane < nch && ox < G.W && oy < G.H) {
+          float* o = opb + (long long)(c0 + lane) * osc + oy * osh + ox;
+          float v = lane == 0 ? acc0 : lane == 1 ? acc1 : lane == 2 ? acc2 : acc3;
+          if (accumulate) v += *o;
+          *o = v;
+        }
+      }
       if (staged) {
         __syncthreads();
         stage ^= 1;
@@ -410,7 +474,6 @@ __global__ void __launch_bounds__(CS_THREADS, 2) bwd_src_csr_kernel(const __grid
                                                                   const __grid_constant__ GradP Q, const WsView ws,
                                                                   const __grid_constant__ CsrArgs A) {
   extern __shared__ float4 cs_smem4[];
-  __shared__ StageTab gtab;
   const Geo& G = P.geo;
   const CsrSmem s = csr_carve(cs_smem4);
   const int d = A.d;
@@ -450,7 +513,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) bwd_src_csr_kernel(const __grid
         __syncthreads();
         for (int h0 = 0; h0 < nhit; h0 += nw) {
           if (nrec + nw * 32 > CS_RC) {
-            csr_flush(P, Q, A, s, gtab, n, t, nrec, nrec, written);
+            csr_flush(P, Q, A, n, t, nrec, nrec, written);
             written = true;
             nrec = nent = 0;
           }
@@ -506,7 +569,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) bwd_src_csr_kernel(const __grid
       __syncthreads();
       for (int h0 = 0; h0 < cnt; h0 += CS_OUTROUND) {
         if (nrec + CS_OUTROUND > CS_RC || (nrec - nin_cur) + CS_OUTROUND > CS_MAXOUT) {
-          csr_flush(P, Q, A, s, gtab, n, t, nrec, nin_cur, written);
+          csr_flush(P, Q, A, n, t, nrec, nin_cur, written);
           written = true;
           nrec = nent = 0;
           nin_cur = 0;
@@ -533,7 +596,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) bwd_src_csr_kernel(const __grid
     }
     // the frame's last batch; also the one that writes zeros when the tile has no contributor at all
     if (nrec > 0 || !written) {
-      csr_flush(P, Q, A, s, gtab, n, t, nrec, nin_cur, written);
+      csr_flush(P, Q, A, n, t, nrec, nin_cur, written);
       written = true;
     }
   }

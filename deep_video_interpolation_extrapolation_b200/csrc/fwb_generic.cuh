@@ -247,4 +247,73 @@ __device__ __forceinline__ void bwdflow_generic_pixel_warp(const Params& P, cons
   }
 }
 
+// Slow-pixel bodies of the staged kernels: the taps were computed once per pixel into shared memory (`k`).
+// Kernel 1: one (pixel, flattened channel) item.
+template <int NDIRS>
+__device__ __forceinline__ void fwd_slow_item(const Params& P, int n, int t, int i, int j, const Tap* k, int cf) {
+  int g, c;
+  chan_lookup(P, cf, g, c);
+  const GroupP& R = P.grp[g];
+  float r = 0.0f;
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const float* s = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d];
+    float a = bilinear(s, k[d].y0 * R.src_sh[d] + k[d].x0, R.src_sh[d], k[d].valid, __fmul_rn(k[d].ux, k[d].uy),
+                       __fmul_rn(k[d].tx, k[d].uy), __fmul_rn(k[d].ux, k[d].ty), __fmul_rn(k[d].tx, k[d].ty));
+    if (P.dir[d].blend != nullptr) a = __fmul_rn(a, k[d].blend);
+    r = (d == 0) ? a : __fadd_rn(r, a);
+  }
+  __stcs(R.out + n * R.out_sn + t * R.out_st + (long long)c * R.out_sc + (long long)i * R.out_sh + j, r);
+}
+
+// Kernel 2: one pixel per warp, lane l takes channels l, l+32, ...; fixed butterfly order (deterministic).
+template <int NDIRS>
+__device__ __forceinline__ void bwdflow_slow_warp(const Params& P, const GradP& Q, int n, int t, int i, int j, const Tap* k) {
+  const Geo& G = P.geo;
+  const int lane = threadIdx.x & 31;
+  float gix[NDIRS], giy[NDIRS], gbl[NDIRS];
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    gix[d] = giy[d] = gbl[d] = 0.0f;
+    has_bl[d] = P.dir[d].blend != nullptr;
+  }
+  int Ctot = 0;
+  for (int g = 0; g < G.n_groups; ++g) Ctot += P.grp[g].C;
+  for (int cf = lane; cf < Ctot; cf += 32) {
+    int g, c;
+    chan_lookup(P, cf, g, c);
+    if (!Q.grad_out[g]) continue;
+    const GroupP& R = P.grp[g];
+    const float gout = __ldg(Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)c * Q.go_sc[g] +
+                             (long long)i * Q.go_sh[g] + j);
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      const int sh = R.src_sh[d];
+      const float* sp = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d] + k[d].y0 * sh + k[d].x0;
+      const unsigned v = k[d].valid;
+      const float a = ldg_if(sp, v & 1u), b = ldg_if(sp + 1, v & 2u);
+      const float cc = ldg_if(sp + sh, v & 4u), dd = ldg_if(sp + sh + 1, v & 8u);
+      float gw = gout;
+      if (has_bl[d]) {
+        const float top = fmaf(b, k[d].tx, a * k[d].ux), bot = fmaf(dd, k[d].tx, cc * k[d].ux);
+        gbl[d] = fmaf(gout, fmaf(bot, k[d].ty, top * k[d].uy), gbl[d]);
+        gw = gout * k[d].blend;
+      }
+      gix[d] = fmaf(gw, fmaf(k[d].ty, dd - cc, k[d].uy * (b - a)), gix[d]);
+      giy[d] = fmaf(gw, fmaf(k[d].tx, dd - b, k[d].ux * (cc - a)), giy[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gix[d] += __shfl_xor_sync(0xffffffffu, gix[d], o);
+      giy[d] += __shfl_xor_sync(0xffffffffu, giy[d], o);
+      gbl[d] += __shfl_xor_sync(0xffffffffu, gbl[d], o);
+    }
+    if (lane == 0) bwdflow_store(P, Q, d, n, t, i, j, k[d], gix[d], giy[d], gbl[d]);
+  }
+}
+
 }  // namespace fwb
