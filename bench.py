@@ -36,7 +36,8 @@ CH = (3, 20)  # RGB + 20-class seg
 C_TOTAL = sum(CH)
 BYTES_PER_PIX = 32 * C_TOTAL + 72  # bidirectional warp+blend fwd+bwd, fp32
 # per-kernel algorithmic bytes/pixel when the three kernels run as separate launches
-KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48, "backward_src": 12 * C_TOTAL + 24}
+KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48, "backward_src": 12 * C_TOTAL + 24,
+                "backward_fused": 20 * C_TOTAL + 48}
 
 
 def peaks():
@@ -224,8 +225,10 @@ class CabiStep:
         ptr, st = (lambda t: t.data_ptr()), (lambda t: t.stride())
         self.p = fill_problem(N=N, T=1, H=H, W=W, flows=flows, gates=[None, None], blends=blends, signs=[-1.0, 1.0], srcs=srcs,
                               outs=self.outs, padding_mode=L.FWB_PAD_BORDER if pad == "border" else L.FWB_PAD_ZEROS,
-                              align_corners=False, flags=(L.FWB_FLAG_DETERMINISTIC if deterministic else 0) |
-                              (L.FWB_FLAG_ATOMIC_SRC if atomic_src else 0), ptr=ptr, strides=st)
+                              align_corners=False,
+                              flags=(L.FWB_FLAG_DETERMINISTIC if deterministic else
+                                     (L.FWB_FLAG_ATOMIC_SRC if atomic_src else L.FWB_FLAG_FUSED_BWD)), ptr=ptr, strides=st)
+        self.fused = not deterministic and not atomic_src
         self.q = fill_grads(self.p, grad_outs=gos, grad_srcs=self.g_srcs, grad_flows=self.g_flows, grad_gates=[None, None],
                             grad_blends=self.g_blends, ptr=ptr, strides=st)
         self.keep += [flows, blends, srcs, gos]
@@ -323,7 +326,11 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     # ---- per-kernel durations (same buffers, CUDA events on the launching stream)
     kt = {}
     ksteps = max(10, min(args.steps, 100))
-    for name, fn in (("forward", step.forward), ("backward_flow", step.backward_flow), ("backward_src", step.backward_src)):
+    if step.fused:  # kernels 2+3 run as one fused launch inside the backward_flow entry point
+        klist = (("forward", step.forward), ("backward_fused", step.backward_flow))
+    else:
+        klist = (("forward", step.forward), ("backward_flow", step.backward_flow), ("backward_src", step.backward_src))
+    for name, fn in klist:
         kt[name] = timed(fn, ksteps, 3, sync) / ksteps
 
     # ---- e2e: public autograd API, HOST (pinned) buffers, H2D + D2H inside the timed region
@@ -377,7 +384,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "kernels": kernels,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "deep_video_interpolation_extrapolation_b200.warp_blend + torch.autograd.backward, pinned host buffers"},
-            "gpu_launches": args.steps * chain * LAUNCHES_PER_STEP[bool(args.deterministic)],
+            "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -392,7 +399,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
 
 
 # launches of OUR kernels per step (forward 1, backward_flow 1, backward_src: see csrc/flowwarp_b200.cu)
-LAUNCHES_PER_STEP = {False: 1 + 1 + (4 + 1), True: 1 + 1 + (4 + 1)}
+# fused: forward 1 + zero grad_src 4 + fused backward 1; split: forward 1 + (table init 1 + emit 1 + kernel 2) + kernel 3 x2
+LAUNCHES_PER_STEP = {"fused": 1 + 4 + 1, "split": 1 + 3 + 2}
 
 
 def main():

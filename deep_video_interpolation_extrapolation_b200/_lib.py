@@ -13,6 +13,7 @@ FWB_MAX_GROUPS = 4
 FWB_PAD_ZEROS, FWB_PAD_BORDER = 0, 1
 FWB_FLAG_DETERMINISTIC = 1
 FWB_FLAG_ATOMIC_SRC = 2  # grad_src by global atomics (ATen-style), for A/B measurements only
+FWB_FLAG_FUSED_BWD = 4  # backward_flow also produces grad_src (fused kernels 2+3, non-deterministic fast path)
 
 _f32p = C.POINTER(C.c_float)
 i64 = C.c_int64

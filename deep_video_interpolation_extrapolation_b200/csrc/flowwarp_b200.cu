@@ -312,141 +312,8 @@ static int set_smem(K kernel, int bytes) {
 
 using namespace fwb;
 
-extern "C" {
-
-int32_t fwb_version(void) { return FWB_VERSION; }
-
-const char* fwb_strerror(int32_t code) {
-  if (code > 0) return cudaGetErrorString((cudaError_t)code);
-  switch (code) {
-    case 0: return "ok";
-    case FWB_E_NULL: return "a required pointer is NULL";
-    case FWB_E_SHAPE: return "N/T/H/W/C out of range (empty spatial dims are an error)";
-    case FWB_E_DIRS: return "n_dirs must be 1 or 2";
-    case FWB_E_GROUPS: return "n_groups must be in 1..FWB_MAX_GROUPS";
-    case FWB_E_MODE: return "unknown padding_mode / align_corners / sign";
-    case FWB_E_ALIGN: return "pointer not 4-byte aligned";
-    case FWB_E_WORKSPACE: return "workspace missing or too small";
-    case FWB_E_RANGE: return "H or W above 32767";
-    default: return "unknown error";
-  }
-}
-
-int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
-  int rc = validate(p);
-  if (rc) return rc;
-  for (int g = 0; g < p->n_groups; ++g) {
-    if (!p->grp[g].out) return FWB_E_NULL;
-    if ((uintptr_t)p->grp[g].out & 3u) return FWB_E_ALIGN;
-  }
-  if (p->N == 0) return 0;
-  Params P;
-  to_params(p, P);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (stage_ok(p)) {
-    const int sb = stage_smem_bytes();
-#define FWB_LAUNCH_FWD(D, A, B)                                                      \
-  do {                                                                               \
-    if ((rc = set_smem(fwd_pair_kernel<D, A, B>, sb))) return rc;                    \
-    fwd_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, sb / 4);       \
-  } while (0)
-    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
-    switch (key) {
-      case 0: FWB_LAUNCH_FWD(1, false, false); break;
-      case 1: FWB_LAUNCH_FWD(1, false, true); break;
-      case 2: FWB_LAUNCH_FWD(1, true, false); break;
-      case 3: FWB_LAUNCH_FWD(1, true, true); break;
-      case 4: FWB_LAUNCH_FWD(2, false, false); break;
-      case 5: FWB_LAUNCH_FWD(2, false, true); break;
-      case 6: FWB_LAUNCH_FWD(2, true, false); break;
-      default: FWB_LAUNCH_FWD(2, true, true); break;
-    }
-#undef FWB_LAUNCH_FWD
-    return (int32_t)cudaGetLastError();
-  }
-  const dim3 grid = pixel_grid(p), block(NTHREADS);
-  if (p->n_dirs == 2)
-    fwd_kernel<2><<<grid, block, 0, s>>>(P);
-  else
-    fwd_kernel<1><<<grid, block, 0, s>>>(P);
-  return (int32_t)cudaGetLastError();
-}
-
-int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0, uint8_t* valid,
-                           float* ix, float* iy, void* stream) {
-  int rc = validate(p);
-  if (rc) return rc;
-  if (d < 0 || d >= p->n_dirs) return FWB_E_DIRS;
-  if (p->N == 0) return 0;
-  Params P;
-  to_params(p, P);
-  indices_kernel<<<pixel_grid(p), dim3(NTHREADS), 0, (cudaStream_t)stream>>>(P, d, x0, y0, valid, ix, iy);
-  return (int32_t)cudaGetLastError();
-}
-
-size_t fwb_workspace_bytes(const fwb_problem* p) {
-  if (validate(p)) return 0;
-  return ws_layout(p->n_dirs, (long long)p->N * p->T, p->H, p->W).total;
-}
-
-int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
-  int rc = validate(p);
-  if (rc) return rc;
-  Params P;
-  GradP Q;
-  to_params(p, P);
-  rc = to_grads(p, g, Q);
-  if (rc) return rc;
-  if (p->N == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int NT = p->N * p->T;
-  // the segment tables kernel 3 needs are produced whenever a workspace is supplied
-  if (workspace && !(p->flags & FWB_FLAG_ATOMIC_SRC)) {
-    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
-    if (workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
-    const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
-    const int nh = p->n_dirs * NT;
-    ws_init_kernel<<<(nh + 255) / 256, 256, 0, s>>>(ws.hdr, nh);
-    const dim3 eg((p->W + 31) / 32, (p->H + 7) / 8, NT);
-    if (p->n_dirs == 2)
-      emit_kernel<2><<<eg, 256, 0, s>>>(P, ws);
-    else
-      emit_kernel<1><<<eg, 256, 0, s>>>(P, ws);
-  }
-  int want = 0;
-  for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
-  if (want && stage_ok(p)) {
-    const int sb = stage_smem_bytes();
-#define FWB_LAUNCH_BWF(D, A, B)                                                         \
-  do {                                                                                  \
-    if ((rc = set_smem(bwd_flow_pair_kernel<D, A, B>, sb))) return rc;                  \
-    bwd_flow_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
-  } while (0)
-    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
-    switch (key) {
-      case 0: FWB_LAUNCH_BWF(1, false, false); break;
-      case 1: FWB_LAUNCH_BWF(1, false, true); break;
-      case 2: FWB_LAUNCH_BWF(1, true, false); break;
-      case 3: FWB_LAUNCH_BWF(1, true, true); break;
-      case 4: FWB_LAUNCH_BWF(2, false, false); break;
-      case 5: FWB_LAUNCH_BWF(2, false, true); break;
-      case 6: FWB_LAUNCH_BWF(2, true, false); break;
-      default: FWB_LAUNCH_BWF(2, true, true); break;
-    }
-#undef FWB_LAUNCH_BWF
-  } else if (want) {
-    const dim3 grid = pixel_grid(p), block(NTHREADS);
-    if (p->n_dirs == 2)
-      bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
-    else
-      bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
-  }
-  return (int32_t)cudaGetLastError();
-}
-
-int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+static int32_t run_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   int rc = validate(p);
   if (rc) return rc;
   Params P;
@@ -561,6 +428,199 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
   else
     bwd_src_atomic_kernel<1><<<grid, block, 0, s>>>(P, Q);
   return (int32_t)cudaGetLastError();
+}
+
+extern "C" {
+
+int32_t fwb_version(void) { return FWB_VERSION; }
+
+const char* fwb_strerror(int32_t code) {
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case 0: return "ok";
+    case FWB_E_NULL: return "a required pointer is NULL";
+    case FWB_E_SHAPE: return "N/T/H/W/C out of range (empty spatial dims are an error)";
+    case FWB_E_DIRS: return "n_dirs must be 1 or 2";
+    case FWB_E_GROUPS: return "n_groups must be in 1..FWB_MAX_GROUPS";
+    case FWB_E_MODE: return "unknown padding_mode / align_corners / sign";
+    case FWB_E_ALIGN: return "pointer not 4-byte aligned";
+    case FWB_E_WORKSPACE: return "workspace missing or too small";
+    case FWB_E_RANGE: return "H or W above 32767";
+    default: return "unknown error";
+  }
+}
+
+int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  for (int g = 0; g < p->n_groups; ++g) {
+    if (!p->grp[g].out) return FWB_E_NULL;
+    if ((uintptr_t)p->grp[g].out & 3u) return FWB_E_ALIGN;
+  }
+  if (p->N == 0) return 0;
+  Params P;
+  to_params(p, P);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (stage_ok(p)) {
+    const int sb = stage_smem_bytes();
+#define FWB_LAUNCH_FWD(D, A, B)                                                      \
+  do {                                                                               \
+    if ((rc = set_smem(fwd_pair_kernel<D, A, B>, sb))) return rc;                    \
+    fwd_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, sb / 4);       \
+  } while (0)
+    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+    switch (key) {
+      case 0: FWB_LAUNCH_FWD(1, false, false); break;
+      case 1: FWB_LAUNCH_FWD(1, false, true); break;
+      case 2: FWB_LAUNCH_FWD(1, true, false); break;
+      case 3: FWB_LAUNCH_FWD(1, true, true); break;
+      case 4: FWB_LAUNCH_FWD(2, false, false); break;
+      case 5: FWB_LAUNCH_FWD(2, false, true); break;
+      case 6: FWB_LAUNCH_FWD(2, true, false); break;
+      default: FWB_LAUNCH_FWD(2, true, true); break;
+    }
+#undef FWB_LAUNCH_FWD
+    return (int32_t)cudaGetLastError();
+  }
+  const dim3 grid = pixel_grid(p), block(NTHREADS);
+  if (p->n_dirs == 2)
+    fwd_kernel<2><<<grid, block, 0, s>>>(P);
+  else
+    fwd_kernel<1><<<grid, block, 0, s>>>(P);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0, uint8_t* valid,
+                           float* ix, float* iy, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if (d < 0 || d >= p->n_dirs) return FWB_E_DIRS;
+  if (p->N == 0) return 0;
+  Params P;
+  to_params(p, P);
+  indices_kernel<<<pixel_grid(p), dim3(NTHREADS), 0, (cudaStream_t)stream>>>(P, d, x0, y0, valid, ix, iy);
+  return (int32_t)cudaGetLastError();
+}
+
+size_t fwb_workspace_bytes(const fwb_problem* p) {
+  if (validate(p)) return 0;
+  return ws_layout(p->n_dirs, (long long)p->N * p->T, p->H, p->W).total;
+}
+
+int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  Params P;
+  GradP Q;
+  to_params(p, P);
+  rc = to_grads(p, g, Q);
+  if (rc) return rc;
+  if (p->N == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int NT = p->N * p->T;
+  const bool fused_req = (p->flags & FWB_FLAG_FUSED_BWD) && !(p->flags & (FWB_FLAG_DETERMINISTIC | FWB_FLAG_ATOMIC_SRC));
+  if (fused_req) {
+    bool any_src = false, ok = stage_ok(p) && env_int("FWB_NOFUSE", 0) == 0;
+    for (int gi = 0; gi < p->n_groups; ++gi)
+      for (int d = 0; d < p->n_dirs; ++d) {
+        if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
+        any_src = true;
+        if (((uintptr_t)Q.grad_src[gi][d] & 15u) || (Q.gs_sn[gi][d] & 3) || (Q.gs_st[gi][d] & 3) || (Q.gs_sc[gi][d] & 3) ||
+            (Q.gs_sh[gi][d] & 3))
+          ok = false;  // red.global.add.v4.f32 needs 16-byte aligned rows
+      }
+    if (ok && any_src) {
+      // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out)
+      for (int gi = 0; gi < p->n_groups; ++gi)
+        for (int d = 0; d < p->n_dirs; ++d) {
+          float* gs = Q.grad_src[gi][d];
+          if (!gs) continue;
+          const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
+          const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
+          zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d], p->N, Tn,
+                                              p->grp[gi].C, p->H, p->W);
+        }
+      const int sb = env_int("FWB_FUSED_KB", 100) * 1024;
+#define FWB_LAUNCH_FUSED(D, A, B)                                                        \
+  do {                                                                                   \
+    if ((rc = set_smem(bwd_fused_pair_kernel<D, A, B>, sb))) return rc;                  \
+    bwd_fused_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
+  } while (0)
+      const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+      switch (key) {
+        case 0: FWB_LAUNCH_FUSED(1, false, false); break;
+        case 1: FWB_LAUNCH_FUSED(1, false, true); break;
+        case 2: FWB_LAUNCH_FUSED(1, true, false); break;
+        case 3: FWB_LAUNCH_FUSED(1, true, true); break;
+        case 4: FWB_LAUNCH_FUSED(2, false, false); break;
+        case 5: FWB_LAUNCH_FUSED(2, false, true); break;
+        case 6: FWB_LAUNCH_FUSED(2, true, false); break;
+        default: FWB_LAUNCH_FUSED(2, true, true); break;
+      }
+#undef FWB_LAUNCH_FUSED
+      return (int32_t)cudaGetLastError();
+    }
+  }
+  // the segment tables kernel 3 needs are produced whenever a workspace is supplied
+  if (workspace && !(p->flags & FWB_FLAG_ATOMIC_SRC)) {
+    const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
+    const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
+    const int nh = p->n_dirs * NT;
+    ws_init_kernel<<<(nh + 255) / 256, 256, 0, s>>>(ws.hdr, nh);
+    const dim3 eg((p->W + 31) / 32, (p->H + 7) / 8, NT);
+    if (p->n_dirs == 2)
+      emit_kernel<2><<<eg, 256, 0, s>>>(P, ws);
+    else
+      emit_kernel<1><<<eg, 256, 0, s>>>(P, ws);
+  }
+  int want = 0;
+  for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
+  if (want && stage_ok(p)) {
+    const int sb = stage_smem_bytes();
+#define FWB_LAUNCH_BWF(D, A, B)                                                         \
+  do {                                                                                  \
+    if ((rc = set_smem(bwd_flow_pair_kernel<D, A, B>, sb))) return rc;                  \
+    bwd_flow_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
+  } while (0)
+    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+    switch (key) {
+      case 0: FWB_LAUNCH_BWF(1, false, false); break;
+      case 1: FWB_LAUNCH_BWF(1, false, true); break;
+      case 2: FWB_LAUNCH_BWF(1, true, false); break;
+      case 3: FWB_LAUNCH_BWF(1, true, true); break;
+      case 4: FWB_LAUNCH_BWF(2, false, false); break;
+      case 5: FWB_LAUNCH_BWF(2, false, true); break;
+      case 6: FWB_LAUNCH_BWF(2, true, false); break;
+      default: FWB_LAUNCH_BWF(2, true, true); break;
+    }
+#undef FWB_LAUNCH_BWF
+  } else if (want) {
+    const dim3 grid = pixel_grid(p), block(NTHREADS);
+    if (p->n_dirs == 2)
+      bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
+    else
+      bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+  }
+  if ((rc = (int32_t)cudaGetLastError())) return rc;
+  if (fused_req) {  // the fused kernel could not take this problem: finish grad_src here, as the flag promises
+    bool any_src = false;
+    for (int gi = 0; gi < p->n_groups; ++gi)
+      for (int d = 0; d < p->n_dirs; ++d) any_src |= Q.grad_src[gi][d] != nullptr;
+    if (any_src) return run_backward_src(p, g, workspace, workspace_bytes, stream);
+  }
+  return 0;
+}
+
+int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  // with FWB_FLAG_FUSED_BWD the backward_flow call has already produced grad_src
+  if (p && (p->flags & FWB_FLAG_FUSED_BWD) && !(p->flags & (FWB_FLAG_DETERMINISTIC | FWB_FLAG_ATOMIC_SRC))) {
+    const int rc = validate(p);
+    return rc;
+  }
+  return run_backward_src(p, g, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -519,4 +519,310 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_flow_pair_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kernels 2 + 3 FUSED (the default, non-deterministic backward): gradient w.r.t. flow / gate / blend AND
+// w.r.t. the sources in one pass over grad_out.
+//
+// The image-gradient scatter of a tile lands exactly on the cells the tile gathers from — its row-segment
+// footprint — so it is accumulated in a shared-memory copy of that footprint and only the footprint (1.3-1.4
+// cells per pixel, not 4 taps per pixel) goes to global memory, as 16-byte vector reductions
+// (red.global.add.v4.f32) into the zero-initialised grad_src.  B200 has no native fp32 shared-memory atomic
+// (atomicAdd(float*) on shared compiles to a CAS spin loop, 2-3x slower than ATOMS.ADD), so the tile accumulates
+// in int32 FIXED POINT: per channel pair the CTA takes amax = max |grad_out * blend| over its pixels and scales
+// by 2^(20 - exponent(amax)); a contribution w * g (|w| <= 1) is then below 2^21, so the 512 pixels of a tile
+// cannot overflow int32 whatever the flow does, and the rounding error is 2^-21 of amax per contribution.
+// A pair whose amax is not finite takes plain global float atomics, so inf / NaN gradients still propagate.
+// The order of the global reductions varies from run to run: this is the NON-DETERMINISTIC mode; the
+// deterministic mode is kernel 2 followed by the owner gather (fwb_owner.cuh / fwb_csr.cuh).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// global-atomic scatter of one pixel's 4 taps of one direction for channels c (and c+1)
+__device__ __forceinline__ void scatter_atomic_px(const GradP& Q, int g, int d, int n, int t, int c, bool two, const Tap& k, float gw0,
+                                                  float gw1) {
+  float* gs = Q.grad_src[g][d];
+  if (!gs) return;
+  const int sh = Q.gs_sh[g][d];
+  gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d] + (long long)k.y0 * sh + k.x0;
+  const float w[4] = {k.ux * k.uy, k.tx * k.uy, k.ux * k.ty, k.tx * k.ty};
+  const int off[4] = {0, 1, sh, sh + 1};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (k.valid & (1u << q)) {
+      atomicAdd(gs + off[q], w[q] * gw0);
+      if (two) atomicAdd(gs + off[q] + Q.gs_sc[g][d], w[q] * gw1);
+    }
+}
+
+// one pixel, all channels of all groups: kernel 2's generic body + global-atomic scatter (tiles that do not fit)
+template <int NDIRS>
+__device__ __forceinline__ void bwd_fused_generic_pixel(const Params& P, const GradP& Q, int n, int t, int i, int j) {
+  bwdflow_generic_pixel<NDIRS>(P, Q, n, t, i, j);
+  Tap k[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) compute_tap(P.geo, P.dir[d], n, t, i, j, k[d]);
+  for (int g = 0; g < P.geo.n_groups; ++g) {
+    if (!Q.grad_out[g]) continue;
+    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)i * Q.go_sh[g] + j;
+    for (int c = 0; c < P.grp[g].C; ++c) {
+      const float gout = __ldg(go + (long long)c * Q.go_sc[g]);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d)
+        scatter_atomic_px(Q, g, d, n, t, c, false, k[d], P.dir[d].blend ? gout * k[d].blend : gout, 0.f);
+    }
+  }
+}
+
+template <int NDIRS, bool ALIGN, bool BORDER>
+__global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __grid_constant__ Params P,
+                                                                      const __grid_constant__ GradP Q, int smem_floats) {
+  extern __shared__ float4 pr_smem4[];
+  float* const smem = reinterpret_cast<float*>(pr_smem4);
+  __shared__ StageTab tb[NDIRS];
+  __shared__ StageSlow slow;
+  __shared__ Tap slowtap[PR_MAXSLOW][NDIRS];
+  __shared__ unsigned amax_s[2];
+  const Geo& G = P.geo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PairCtx<NDIRS> cx;
+  // memory: 1 gather buffer + 1 accumulator (cells x 8 B each) + 2 scratch stages; the prologue's test assumes
+  // 2 gather buffers + PR_NS (3) stages, which is the same size
+  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, cx);
+  const int n = cx.n, t = cx.t, j = cx.j;
+
+  if (!cx.ok) {
+#pragma unroll
+    for (int q = 0; q < PR_PPT; ++q)
+      if (cx.inimg[q]) bwd_fused_generic_pixel<NDIRS>(P, Q, n, t, cx.irow[q], j);
+    return;
+  }
+  bool has_bl[NDIRS];
+  float blmax[PR_PPT];
+#pragma unroll
+  for (int q = 0; q < PR_PPT; ++q) blmax[q] = 0.f;
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    has_bl[d] = P.dir[d].blend != nullptr;
+#pragma unroll
+    for (int q = 0; q < PR_PPT; ++q) blmax[q] = fmaxf(blmax[q], has_bl[d] ? fabsf(cx.px[q][d].bl) : 1.0f);
+  }
+  unsigned skip = 0u;  // groups without grad_out contribute nothing
+#pragma unroll
+  for (int g = 0; g < FWB_MAX_GROUPS; ++g) skip |= (Q.grad_out[g] == nullptr ? 1u : 0u) << g;
+
+  f32x2 tx2[PR_PPT][NDIRS], ty2[PR_PPT][NDIRS], ux2[PR_PPT][NDIRS], uy2[PR_PPT][NDIRS];
+  float gix[PR_PPT][NDIRS], giy[PR_PPT][NDIRS], gbl[PR_PPT][NDIRS];
+#pragma unroll
+  for (int q = 0; q < PR_PPT; ++q)
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      const PairPix& px = cx.px[q][d];
+      tx2[q][d] = pk2(px.tx, px.tx);
+      ty2[q][d] = pk2(px.ty, px.ty);
+      ux2[q][d] = pk2(px.ux, px.ux);
+      uy2[q][d] = pk2(px.uy, px.uy);
+      gix[q][d] = giy[q][d] = gbl[q][d] = 0.f;
+    }
+  float2* const cells = reinterpret_cast<float2*>(smem);                 // the gather buffer
+  int2* const acc = reinterpret_cast<int2*>(cells + cx.cells);           // the fixed-point accumulator
+  const float4* const scr = reinterpret_cast<const float4*>(cells + 2 * cx.cells);
+  const unsigned scr_s = (unsigned)__cvta_generic_to_shared(scr);
+  const unsigned stage_bytes = 32u * (unsigned)cx.pieces;
+  const f32x2 zero2 = pk2(0.f, 0.f), mone2 = pk2(-1.f, -1.f);
+  for (int k = threadIdx.x; k < cx.cells; k += PR_THREADS) acc[k] = make_int2(0, 0);
+  if (threadIdx.x < 2) amax_s[threadIdx.x] = 0u;
+
+  PairStream<NDIRS> ps;
+  ps.g = 0;
+  ps.enter(P, cx, skip);
+  ps.issue(P, cx, scr_s);  // pair 0
+  __syncthreads();         // slowtap, acc, amax_s
+  // slow pixels, while the first copies are in flight: one warp per pixel, lanes over the channels
+  for (int s = warp; s < slow.n; s += PR_THREADS / 32) {
+    const int pix = slow.pix[s];
+    const int si = blockIdx.y * PR_TH + (pix >> 5), sj = blockIdx.x * PR_TW + (pix & 31);
+    bwdflow_slow_warp<NDIRS>(P, Q, n, t, si, sj, slowtap[s]);
+    int Ctot = 0;
+    for (int g = 0; g < G.n_groups; ++g) Ctot += P.grp[g].C;
+    for (int cf = lane; cf < Ctot; cf += 32) {
+      int g, c;
+      chan_lookup(P, cf, g, c);
+      if (!Q.grad_out[g]) continue;
+      const float gout = __ldg(Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)c * Q.go_sc[g] + (long long)si * Q.go_sh[g] + sj);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d)
+        scatter_atomic_px(Q, g, d, n, t, c, false, slowtap[s][d], has_bl[d] ? gout * slowtap[s][d].blend : gout, 0.f);
+    }
+  }
+  // grad_out of the first pair and its amax
+  float go0[PR_PPT], go1[PR_PPT];
+#pragma unroll
+  for (int q = 0; q < PR_PPT; ++q) go0[q] = go1[q] = 0.f;
+  {
+    int g0 = 0;
+    while (g0 < G.n_groups && ((skip >> g0) & 1u)) ++g0;
+    if (g0 < G.n_groups) {
+      const float* gp = Q.grad_out[g0] + n * Q.go_sn[g0] + t * Q.go_st[g0] + j;
+      float m = 0.f;
+#pragma unroll
+      for (int q = 0; q < PR_PPT; ++q) {
+        const float* gq = gp + (long long)cx.irow[q] * Q.go_sh[g0];
+        go0[q] = cx.act[q] ? __ldcs(gq) : 0.f;
+        go1[q] = (cx.act[q] && P.grp[g0].C > 1) ? __ldcs(gq + Q.go_sc[g0]) : 0.f;
+        const float a0 = fabsf(go0[q]), a1 = fabsf(go1[q]);
+        // NaN must win the max: compare on the bit patterns (non-negative floats order like unsigned ints)
+        m = __uint_as_float(max(__float_as_uint(m), max(__float_as_uint(a0 * blmax[q]), __float_as_uint(a1 * blmax[q]))));
+      }
+      unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+      if (lane == 0) atomicMax(&amax_s[0], mb);
+    }
+  }
+  cp_async_wait<0>();
+  pair_transpose<NDIRS>(cx, scr, cells);
+  __syncthreads();
+  int st_next = 1, pi = 0;  // scratch stage of the next pair; parity of the pair being processed
+  for (int g = 0; g < G.n_groups; ++g) {
+    if ((skip >> g) & 1u) continue;
+    const GroupP& R = P.grp[g];
+    const float* gp = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + j;
+    const int gsc = Q.go_sc[g];
+    bool want[NDIRS];
+    bool any_want = false;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      want[d] = Q.grad_src[g][d] != nullptr;
+      any_want |= want[d];
+    }
+    for (int c = 0; c < R.C; c += 2) {
+      // ---- copies of the next pair; its grad_out and amax
+      if (ps.valid(P)) ps.advance(P, cx, skip);
+      ps.issue(P, cx, scr_s + (unsigned)st_next * stage_bytes);
+      float gn0[PR_PPT], gn1[PR_PPT];
+#pragma unroll
+      for (int q = 0; q < PR_PPT; ++q) gn0[q] = gn1[q] = 0.f;
+      if (ps.valid(P)) {
+        const int g2 = ps.g;
+        const float* gp2 = Q.grad_out[g2] + n * Q.go_sn[g2] + t * Q.go_st[g2] + (long long)ps.c * Q.go_sc[g2] + j;
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < PR_PPT; ++q) {
+          const float* gq = gp2 + (long long)cx.irow[q] * Q.go_sh[g2];
+          gn0[q] = cx.act[q] ? __ldcs(gq) : 0.f;
+          gn1[q] = (cx.act[q] && ps.c + 1 < ps.C) ? __ldcs(gq + Q.go_sc[g2]) : 0.f;
+          const float a0 = fabsf(gn0[q]), a1 = fabsf(gn1[q]);
+          m = __uint_as_float(max(__float_as_uint(m), max(__float_as_uint(a0 * blmax[q]), __float_as_uint(a1 * blmax[q]))));
+        }
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if (lane == 0) atomicMax(&amax_s[pi ^ 1], mb);
+      }
+      // ---- scale of this pair
+      const unsigned ab = amax_s[pi];
+      const bool finite = ab < 0x7f800000u;
+      const int sexp = min(252, max(2, 275 - 21 + 20 - (int)(ab >> 23)));  // biased exponent of 2^(20 - exponent(amax))
+      const float S = __uint_as_float((unsigned)sexp << 23), Sinv = __uint_as_float((unsigned)(254 - sexp) << 23);
+      const bool two = c + 1 < R.C;
+      // ---- gather (kernel 2) + scatter into the accumulator
+#pragma unroll
+      for (int q = 0; q < PR_PPT; ++q) {
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          const PairPix& px = cx.px[q][d];
+          const float2* s0 = cells + px.o0;
+          const float2* s1 = cells + px.o1;
+          const f32x2 a = as2(s0[0]), bq = as2(s0[1]), c_ = as2(s1[0]), dd = as2(s1[1]);
+          float gw0 = go0[q], gw1 = go1[q];
+          if (has_bl[d]) {
+            const f32x2 top = ffma2(bq, tx2[q][d], ffma2(a, ux2[q][d], zero2));
+            const f32x2 bot = ffma2(dd, tx2[q][d], ffma2(c_, ux2[q][d], zero2));
+            const f32x2 val = ffma2(bot, ty2[q][d], ffma2(top, uy2[q][d], zero2));
+            float v0, v1;
+            upk2(val, v0, v1);
+            gbl[q][d] = fmaf(go1[q], v1, fmaf(go0[q], v0, gbl[q][d]));
+            gw0 *= px.bl;
+            gw1 *= px.bl;
+          }
+          const f32x2 dx_top = ffma2(a, mone2, bq), dx_bot = ffma2(c_, mone2, dd);  // b - a, dd - cc
+          const f32x2 dy_rgt = ffma2(bq, mone2, dd), dy_lft = ffma2(a, mone2, c_);  // dd - b, cc - a
+          const f32x2 ex = ffma2(ty2[q][d], dx_bot, ffma2(uy2[q][d], dx_top, zero2));
+          const f32x2 ey = ffma2(tx2[q][d], dy_rgt, ffma2(ux2[q][d], dy_lft, zero2));
+          float ex0, ex1, ey0, ey1;
+          upk2(ex, ex0, ex1);
+          upk2(ey, ey0, ey1);
+          gix[q][d] = fmaf(gw1, ex1, fmaf(gw0, ex0, gix[q][d]));
+          giy[q][d] = fmaf(gw1, ey1, fmaf(gw0, ey0, giy[q][d]));
+          if (want[d] && ab != 0u) {
+            if (finite) {
+              const float s0f = gw0 * S, s1f = gw1 * S;
+              const float w0 = px.ux * px.uy, w1 = px.tx * px.uy, w2 = px.ux * px.ty, w3 = px.tx * px.ty;
+              int* a0 = reinterpret_cast<int*>(acc + px.o0);
+              int* a1 = reinterpret_cast<int*>(acc + px.o1);
+              atomicAdd(a0, __float2int_rn(s0f * w0));
+              atomicAdd(a0 + 1, __float2int_rn(s1f * w0));
+              atomicAdd(a0 + 2, __float2int_rn(s0f * w1));
+              atomicAdd(a0 + 3, __float2int_rn(s1f * w1));
+              atomicAdd(a1, __float2int_rn(s0f * w2));
+              atomicAdd(a1 + 1, __float2int_rn(s1f * w2));
+              atomicAdd(a1 + 2, __float2int_rn(s0f * w3));
+              atomicAdd(a1 + 3, __float2int_rn(s1f * w3));
+            } else if (cx.act[q]) {  // inf / NaN in grad_out: exact float atomics straight to global memory
+              Tap k;
+              compute_tap(G, P.dir[d], n, t, cx.irow[q], j, k);
+              scatter_atomic_px(Q, g, d, n, t, c, two, k, gw0, gw1);
+            }
+          }
+        }
+      }
+      cp_async_wait<0>();  // this thread's copies of the next pair have landed
+      __syncthreads();     // (A) everyone is done with the gather buffer and with the scatter
+      pair_transpose<NDIRS>(cx, scr + (size_t)st_next * 2 * cx.pieces, cells);
+      st_next ^= 1;
+      // ---- flush the accumulator: this thread's in-image pieces -> red.v4 into grad_src, then zero them
+      if (any_want && ab != 0u && finite) {
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          if (!want[d]) continue;
+          float* gsp = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d];
+          int4* ap = reinterpret_cast<int4*>(acc + (d == 0 ? 0 : cx.slot[0]) + ST_ZPAD);
+#pragma unroll
+          for (int s = 0; s < PR_SLOTS; ++s)
+            if (cx.ld[d].bytes[s] == 16) {
+              const int k = threadIdx.x + s * PR_THREADS;
+              const int4 u = ap[2 * k], v = ap[2 * k + 1];  // {c0,d0,c1,d1} {c2,d2,c3,d3}
+              if ((u.x | u.y | u.z | u.w | v.x | v.y | v.z | v.w) != 0) {
+                float* dst = gsp + (long long)(cx.ld[d].ycol[s] >> 16) * Q.gs_sh[g][d] + (cx.ld[d].ycol[s] & 0xffff);
+                if ((u.x | u.z | v.x | v.z) != 0)
+                  red_add_v4(dst, make_float4((float)u.x * Sinv, (float)u.z * Sinv, (float)v.x * Sinv, (float)v.z * Sinv));
+                if (two && (u.y | u.w | v.y | v.w) != 0)
+                  red_add_v4(dst + Q.gs_sc[g][d], make_float4((float)u.y * Sinv, (float)u.w * Sinv, (float)v.y * Sinv, (float)v.w * Sinv));
+                ap[2 * k] = make_int4(0, 0, 0, 0);
+                ap[2 * k + 1] = make_int4(0, 0, 0, 0);
+              }
+            }
+        }
+      }
+      if (threadIdx.x == 0) amax_s[pi] = 0u;
+      __syncthreads();  // (B) gather buffer holds the next pair; accumulator is clean
+      pi ^= 1;
+#pragma unroll
+      for (int q = 0; q < PR_PPT; ++q) {
+        go0[q] = gn0[q];
+        go1[q] = gn1[q];
+      }
+    }
+  }
+
+#pragma unroll
+  for (int q = 0; q < PR_PPT; ++q) {
+    if (!cx.act[q]) continue;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      Tap k;
+      compute_tap(G, P.dir[d], n, t, cx.irow[q], j, k);  // mx, my, fx, fy, gate (cheaper to recompute than to hold)
+      bwdflow_store(P, Q, d, n, t, cx.irow[q], j, k, gix[q][d], giy[q][d], gbl[q][d]);
+    }
+  }
+}
+
 }  // namespace fwb

@@ -28,8 +28,9 @@ ATOMIC_SRC = False
 
 
 def _flags(cfg) -> int:
-    return (L.FWB_FLAG_DETERMINISTIC if cfg.deterministic else 0) | (
-        L.FWB_FLAG_ATOMIC_SRC if (ATOMIC_SRC and not cfg.deterministic) else 0)
+    if cfg.deterministic:
+        return L.FWB_FLAG_DETERMINISTIC
+    return L.FWB_FLAG_ATOMIC_SRC if ATOMIC_SRC else L.FWB_FLAG_FUSED_BWD
 
 
 @dataclass(frozen=True)

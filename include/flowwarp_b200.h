@@ -53,6 +53,9 @@ extern "C" {
 /* flags */
 #define FWB_FLAG_DETERMINISTIC 1u /* grad_src must be bit-exact run to run (the default owner-gather kernel is) */
 #define FWB_FLAG_ATOMIC_SRC 2u    /* grad_src by global atomics (ATen-style scatter; non-deterministic; for A/B runs) */
+#define FWB_FLAG_FUSED_BWD 4u     /* fwb_warp_blend_backward_flow also produces grad_src (kernels 2+3 fused: shared-memory
+                                   * fixed-point tiles + vector reductions, non-deterministic); fwb_warp_blend_backward_src
+                                   * then returns at once.  Ignored with FWB_FLAG_DETERMINISTIC / FWB_FLAG_ATOMIC_SRC. */
 
 /* argument errors (negative return values) */
 #define FWB_E_NULL -1      /* a required pointer is NULL */
