@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/flowwarp_b200.h"
 #include "fwb_coords.cuh"
@@ -274,20 +275,30 @@ static dim3 stage_grid(const fwb_problem* p) {
   return dim3((p->W + PR_TW - 1) / PR_TW, (p->H + PR_TH - 1) / PR_TH, p->N * p->T);
 }
 
-// development knobs (read once): FWB_GENERIC=1 forces the global-gather kernels, FWB_SMEM_KB sets the dynamic
-// shared memory of the staged kernels (default 104 KB -> 2 CTAs per SM)
+// Kernel selection.  Defaults are the fastest measured variants (DESIGN.md "Kernel variants"):
+//   forward            generic one-thread-per-pixel gather           ("pairfwd": shared-memory channel-pair kernel)
+//   backward, fast     kernels 2+3 fused, shared-memory tiles + RED   ("nofuse": split kernels, atomics-free)
+//   backward, determ.  generic kernel 2 + owner-gather kernel 3       ("pairflow": channel-pair kernel 2, "csr": list kernel 3)
+// FWB_KERNELS=<comma separated words> switches variants for A/B measurements and for the tests that keep every
+// variant parity-checked; read on every call (getenv is cheap next to a launch).
+enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u };
+static unsigned knobs() {
+  const char* v = getenv("FWB_KERNELS");
+  if (!v || !*v) return 0u;
+  unsigned k = 0u;
+  if (strstr(v, "pairfwd")) k |= KN_PAIRFWD;
+  if (strstr(v, "pairflow")) k |= KN_PAIRFLOW;
+  if (strstr(v, "csr")) k |= KN_CSR;
+  if (strstr(v, "nofuse")) k |= KN_NOFUSE;
+  if (strstr(v, "generic")) k |= KN_GENERIC;
+  return k;
+}
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
-static int stage_smem_bytes() {
-  static const int kb = env_int("FWB_SMEM_KB", 62);
-  return kb * 1024;
-}
-static bool force_generic() {
-  static const int g = env_int("FWB_GENERIC", 0);
-  return g != 0;
-}
+static int stage_smem_bytes() { return env_int("FWB_SMEM_KB", 62) * 1024; }
+static bool force_generic() { return (knobs() & KN_GENERIC) != 0u; }
 
 // the staged kernels move 16-byte pieces of the source planes with cp.async: every source pointer must be
 // 16-byte aligned and every stride a multiple of 4 elements
@@ -329,7 +340,7 @@ static int32_t run_backward_src(const fwb_problem* p, const fwb_grads* g, void* 
     const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
     if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
     const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
-    if (env_int("FWB_OWNER", 0) == 0) {
+    if (knobs() & KN_CSR) {
       // ---- owner gather over contributor lists (fwb_csr.cuh)
       const int dyn = env_int("FWB_CSR_KB", 110) * 1024;
       if ((size_t)dyn < csr_smem_bytes(0)) return FWB_E_WORKSPACE;
@@ -461,7 +472,7 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   Params P;
   to_params(p, P);
   cudaStream_t s = (cudaStream_t)stream;
-  if (stage_ok(p)) {
+  if ((knobs() & KN_PAIRFWD) && stage_ok(p)) {
     const int sb = stage_smem_bytes();
 #define FWB_LAUNCH_FWD(D, A, B)                                                      \
   do {                                                                               \
@@ -521,7 +532,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   const int NT = p->N * p->T;
   const bool fused_req = (p->flags & FWB_FLAG_FUSED_BWD) && !(p->flags & (FWB_FLAG_DETERMINISTIC | FWB_FLAG_ATOMIC_SRC));
   if (fused_req) {
-    bool any_src = false, ok = stage_ok(p) && env_int("FWB_NOFUSE", 0) == 0;
+    bool any_src = false, ok = stage_ok(p) && !(knobs() & KN_NOFUSE);
     for (int gi = 0; gi < p->n_groups; ++gi)
       for (int d = 0; d < p->n_dirs; ++d) {
         if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
@@ -577,7 +588,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   }
   int want = 0;
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
-  if (want && stage_ok(p)) {
+  if (want && (knobs() & KN_PAIRFLOW) && stage_ok(p)) {
     const int sb = stage_smem_bytes();
 #define FWB_LAUNCH_BWF(D, A, B)                                                         \
   do {                                                                                  \

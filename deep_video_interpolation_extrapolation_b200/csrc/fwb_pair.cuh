@@ -97,7 +97,7 @@ __device__ __forceinline__ void pair_assign(const StageTab& tb, int H, int W, Pa
 
 template <int NDIRS, bool ALIGN, bool BORDER>
 __device__ __forceinline__ void pair_prologue(const Params& P, StageTab* tb, StageSlow& slow, Tap (*slowtap)[NDIRS], float* smem,
-                                              int smem_floats, PairCtx<NDIRS>& cx) {
+                                              int smem_floats, int n_stages, PairCtx<NDIRS>& cx) {
   const Geo& G = P.geo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   cx.j = blockIdx.x * PR_TW + lane;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void pair_prologue(const Params& P, StageTab* tb, Sta
     cx.pieces += tb[d].ok ? tb[d].total4 : 0;
   }
   // 2 gather buffers x cells x float2  +  PR_NS scratch stages x 2 planes x pieces x float4
-  if (4 * cx.cells + PR_NS * 8 * cx.pieces > smem_floats) cx.ok = 0;
+  if (4 * cx.cells + n_stages * 8 * cx.pieces > smem_floats) cx.ok = 0;
   if (!cx.ok) return;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(PR_THREADS, 3) fwd_pair_kernel(const __grid_co
   __shared__ StageSlow slow;
   __shared__ Tap slowtap[PR_MAXSLOW][NDIRS];
   PairCtx<NDIRS> cx;
-  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, cx);
+  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, PR_NS, cx);
   const int n = cx.n, t = cx.t, j = cx.j;
 
   if (!cx.ok) {  // wild flow: the tile's source footprint does not fit -> gather from global memory
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_flow_pair_kernel(const __gr
   const Geo& G = P.geo;
   const int warp = threadIdx.x >> 5;
   PairCtx<NDIRS> cx;
-  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, cx);
+  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, PR_NS, cx);
   const int n = cx.n, t = cx.t, j = cx.j;
 
   if (!cx.ok) {
@@ -587,9 +587,8 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
   const Geo& G = P.geo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PairCtx<NDIRS> cx;
-  // memory: 1 gather buffer + 1 accumulator (cells x 8 B each) + 2 scratch stages; the prologue's test assumes
-  // 2 gather buffers + PR_NS (3) stages, which is the same size
-  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, cx);
+  // memory: 1 gather buffer + 1 accumulator (cells x 8 B each) + 2 scratch stages
+  pair_prologue<NDIRS, ALIGN, BORDER>(P, tb, slow, slowtap, smem, smem_floats, 2, cx);
   const int n = cx.n, t = cx.t, j = cx.j;
 
   if (!cx.ok) {
@@ -690,10 +689,17 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
     const int gsc = Q.go_sc[g];
     bool want[NDIRS];
     bool any_want = false;
+    float* gsp[NDIRS];             // grad_src plane of the current pair's first channel
+    long long gsc2[NDIRS];         // 2 channel strides
+    int gsoff[NDIRS][PR_SLOTS];    // element offset of this thread's pieces inside a grad_src plane
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {
       want[d] = Q.grad_src[g][d] != nullptr;
       any_want |= want[d];
+      gsp[d] = want[d] ? Q.grad_src[g][d] + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] : nullptr;
+      gsc2[d] = 2ll * Q.gs_sc[g][d];
+#pragma unroll
+      for (int sl = 0; sl < PR_SLOTS; ++sl) gsoff[d][sl] = (cx.ld[d].ycol[sl] >> 16) * Q.gs_sh[g][d] + (cx.ld[d].ycol[sl] & 0xffff);
     }
     for (int c = 0; c < R.C; c += 2) {
       // ---- copies of the next pair; its grad_out and amax
@@ -705,17 +711,12 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
       if (ps.valid(P)) {
         const int g2 = ps.g;
         const float* gp2 = Q.grad_out[g2] + n * Q.go_sn[g2] + t * Q.go_st[g2] + (long long)ps.c * Q.go_sc[g2] + j;
-        float m = 0.f;
 #pragma unroll
         for (int q = 0; q < PR_PPT; ++q) {
           const float* gq = gp2 + (long long)cx.irow[q] * Q.go_sh[g2];
           gn0[q] = cx.act[q] ? __ldcs(gq) : 0.f;
           gn1[q] = (cx.act[q] && ps.c + 1 < ps.C) ? __ldcs(gq + Q.go_sc[g2]) : 0.f;
-          const float a0 = fabsf(gn0[q]), a1 = fabsf(gn1[q]);
-          m = __uint_as_float(max(__float_as_uint(m), max(__float_as_uint(a0 * blmax[q]), __float_as_uint(a1 * blmax[q]))));
         }
-        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-        if (lane == 0) atomicMax(&amax_s[pi ^ 1], mb);
       }
       // ---- scale of this pair
       const unsigned ab = amax_s[pi];
@@ -754,18 +755,23 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
           giy[q][d] = fmaf(gw1, ey1, fmaf(gw0, ey0, giy[q][d]));
           if (want[d] && ab != 0u) {
             if (finite) {
-              const float s0f = gw0 * S, s1f = gw1 * S;
+              const f32x2 sg = pk2(gw0 * S, gw1 * S);
               const float w0 = px.ux * px.uy, w1 = px.tx * px.uy, w2 = px.ux * px.ty, w3 = px.tx * px.ty;
               int* a0 = reinterpret_cast<int*>(acc + px.o0);
               int* a1 = reinterpret_cast<int*>(acc + px.o1);
-              atomicAdd(a0, __float2int_rn(s0f * w0));
-              atomicAdd(a0 + 1, __float2int_rn(s1f * w0));
-              atomicAdd(a0 + 2, __float2int_rn(s0f * w1));
-              atomicAdd(a0 + 3, __float2int_rn(s1f * w1));
-              atomicAdd(a1, __float2int_rn(s0f * w2));
-              atomicAdd(a1 + 1, __float2int_rn(s1f * w2));
-              atomicAdd(a1 + 2, __float2int_rn(s0f * w3));
-              atomicAdd(a1 + 3, __float2int_rn(s1f * w3));
+              float v0, v1;
+              upk2(ffma2(sg, pk2(w0, w0), zero2), v0, v1);
+              atomicAdd(a0, __float2int_rn(v0));
+              atomicAdd(a0 + 1, __float2int_rn(v1));
+              upk2(ffma2(sg, pk2(w1, w1), zero2), v0, v1);
+              atomicAdd(a0 + 2, __float2int_rn(v0));
+              atomicAdd(a0 + 3, __float2int_rn(v1));
+              upk2(ffma2(sg, pk2(w2, w2), zero2), v0, v1);
+              atomicAdd(a1, __float2int_rn(v0));
+              atomicAdd(a1 + 1, __float2int_rn(v1));
+              upk2(ffma2(sg, pk2(w3, w3), zero2), v0, v1);
+              atomicAdd(a1 + 2, __float2int_rn(v0));
+              atomicAdd(a1 + 3, __float2int_rn(v1));
             } else if (cx.act[q]) {  // inf / NaN in grad_out: exact float atomics straight to global memory
               Tap k;
               compute_tap(G, P.dir[d], n, t, cx.irow[q], j, k);
@@ -773,6 +779,17 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
             }
           }
         }
+      }
+      {  // amax of the next pair (its grad_out has had the whole gather to arrive)
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < PR_PPT; ++q) {
+          const float a0 = fabsf(gn0[q]) * blmax[q], a1 = fabsf(gn1[q]) * blmax[q];
+          // NaN must win the max: compare on the bit patterns (non-negative floats order like unsigned ints)
+          m = __uint_as_float(max(__float_as_uint(m), max(__float_as_uint(a0), __float_as_uint(a1))));
+        }
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if (lane == 0 && mb != 0u) atomicMax(&amax_s[pi ^ 1], mb);
       }
       cp_async_wait<0>();  // this thread's copies of the next pair have landed
       __syncthreads();     // (A) everyone is done with the gather buffer and with the scatter
@@ -783,25 +800,28 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_fused_pair_kernel(const __g
 #pragma unroll
         for (int d = 0; d < NDIRS; ++d) {
           if (!want[d]) continue;
-          float* gsp = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d];
           int4* ap = reinterpret_cast<int4*>(acc + (d == 0 ? 0 : cx.slot[0]) + ST_ZPAD);
 #pragma unroll
-          for (int s = 0; s < PR_SLOTS; ++s)
-            if (cx.ld[d].bytes[s] == 16) {
-              const int k = threadIdx.x + s * PR_THREADS;
+          for (int sl = 0; sl < PR_SLOTS; ++sl)
+            if (cx.ld[d].bytes[sl] == 16) {
+              const int k = threadIdx.x + sl * PR_THREADS;
               const int4 u = ap[2 * k], v = ap[2 * k + 1];  // {c0,d0,c1,d1} {c2,d2,c3,d3}
-              if ((u.x | u.y | u.z | u.w | v.x | v.y | v.z | v.w) != 0) {
-                float* dst = gsp + (long long)(cx.ld[d].ycol[s] >> 16) * Q.gs_sh[g][d] + (cx.ld[d].ycol[s] & 0xffff);
-                if ((u.x | u.z | v.x | v.z) != 0)
+              const int nz0 = u.x | u.z | v.x | v.z, nz1 = u.y | u.w | v.y | v.w;
+              if ((nz0 | nz1) != 0) {
+                float* dst = gsp[d] + gsoff[d][sl];
+                if (nz0 != 0)
                   red_add_v4(dst, make_float4((float)u.x * Sinv, (float)u.z * Sinv, (float)v.x * Sinv, (float)v.z * Sinv));
-                if (two && (u.y | u.w | v.y | v.w) != 0)
-                  red_add_v4(dst + Q.gs_sc[g][d], make_float4((float)u.y * Sinv, (float)u.w * Sinv, (float)v.y * Sinv, (float)v.w * Sinv));
+                if (two && nz1 != 0)
+                  red_add_v4(dst + (gsc2[d] >> 1), make_float4((float)u.y * Sinv, (float)u.w * Sinv, (float)v.y * Sinv, (float)v.w * Sinv));
                 ap[2 * k] = make_int4(0, 0, 0, 0);
                 ap[2 * k + 1] = make_int4(0, 0, 0, 0);
               }
             }
         }
       }
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d)
+        if (want[d]) gsp[d] += gsc2[d];
       if (threadIdx.x == 0) amax_s[pi] = 0u;
       __syncthreads();  // (B) gather buffer holds the next pair; accumulator is clean
       pi ^= 1;
