@@ -40,6 +40,16 @@ KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48
                 "backward_fused": 20 * C_TOTAL + 48}
 
 
+def ncu_traffic(kernel, cfg_id):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum); None when no capture exists for this kernel and workload."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(f"config{cfg_id}", {}).get(kernel)
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -312,11 +322,9 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     sync()
     if sampler:
         sampler.mark("timed_end")
-    el = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    el = float(el)
-    value = world * pix_step * args.steps / el / 1e9
+    from deep_video_interpolation_extrapolation_b200 import sharding
+    el = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)  # the job's step time is the slowest rank's device time
+    value = sharding.job_throughput(pix_step, args.steps, el, world) / 1e9
 
     if args.profile:
         if sampler:
@@ -352,11 +360,9 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             h.copy_(t, non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_el = torch.tensor([timed(e2e_step, e2e_steps, 2, sync)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_el, op=dist.ReduceOp.MAX)
+    e2e_el = sharding.max_over_ranks(timed(e2e_step, e2e_steps, 2, sync), dev)
     d2h = sum(t.numel() * 4 for t in host_out)
-    e2e_val = world * cfg["N"] * cfg["H"] * cfg["W"] * e2e_steps / float(e2e_el) / 1e9
+    e2e_val = sharding.job_throughput(cfg["N"] * cfg["H"] * cfg["W"], e2e_steps, e2e_el, world) / 1e9
     if sampler:
         sampler.mark("load_end")
     clocks = sampler.stop() if sampler else None
@@ -377,7 +383,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
                        "deterministic": bool(args.deterministic), "parallelism": f"batch-sharded x{world}, no collective in the op",
                        "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_pixel": KERNEL_BYTES[dom]},
             "roofline_step": {"bytes_per_pixel": BYTES_PER_PIX, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},

@@ -1,0 +1,47 @@
+"""Batch sharding of the warp over the GPUs of one box.
+
+The op has no cross-sample term (utils/net_utils.py:93-114 warps every sample with its own flow), so the
+multi-GPU path is the reference's own: contiguous batch slices, one process per GPU, exactly what its
+DistributedSampler + `batch_size // gpus` does (runners/InterTrainer.py:84-87, main.py:154).  No collective is
+issued by the op; the helpers below are the host logic bench.py and the tests share.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+
+def batch_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """[start, stop) of the samples rank `rank` of `world` owns: contiguous, sizes differ by at most one,
+    earlier ranks take the remainder (empty slices are legal: the op accepts N == 0)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    if n < 0:
+        raise ValueError("negative batch")
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard(tensors: Sequence, rank: int, world: int):
+    """Slice every tensor of a clip batch along dim 0 with `batch_slice` (views, no copies)."""
+    if not tensors:
+        return []
+    a, b = batch_slice(tensors[0].shape[0], rank, world)
+    return [t[a:b] for t in tensors]
+
+
+def max_over_ranks(seconds: float, device=None) -> float:
+    """Step time of the job = the slowest rank's device time (bench.py's timing rule).  No-op without a process
+    group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(seconds)
+    t = torch.tensor([seconds], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def job_throughput(units_per_rank: float, steps: int, seconds_max: float, world: int) -> float:
+    """Whole-job units per second under weak scaling: every rank processes `units_per_rank` per step."""
+    return world * units_per_rank * steps / seconds_max
