@@ -18,6 +18,7 @@
 #include "fwb_stage.cuh"
 #include "fwb_pair.cuh"
 #include "fwb_csr.cuh"
+#include "fwb_tile.cuh"
 
 namespace fwb {
 
@@ -281,7 +282,7 @@ static dim3 stage_grid(const fwb_problem* p) {
 //   backward, determ.  generic kernel 2 + owner-gather kernel 3       ("pairflow": channel-pair kernel 2, "csr": list kernel 3)
 // FWB_KERNELS=<comma separated words> switches variants for A/B measurements and for the tests that keep every
 // variant parity-checked; read on every call (getenv is cheap next to a launch).
-enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u };
+enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_PAIRBWD = 64u };
 static unsigned knobs() {
   const char* v = getenv("FWB_KERNELS");
   if (!v || !*v) return 0u;
@@ -291,6 +292,8 @@ static unsigned knobs() {
   if (strstr(v, "csr")) k |= KN_CSR;
   if (strstr(v, "nofuse")) k |= KN_NOFUSE;
   if (strstr(v, "generic")) k |= KN_GENERIC;
+  if (strstr(v, "notile")) k |= KN_NOTILE;
+  if (strstr(v, "pairbwd")) k |= KN_PAIRBWD;
   return k;
 }
 static int env_int(const char* name, int dflt) {
@@ -312,6 +315,51 @@ static bool stage_ok(const fwb_problem* p) {
         return false;
     }
   return true;
+}
+
+static int total_channels(const fwb_problem* p) {
+  int c = 0;
+  for (int g = 0; g < p->n_groups; ++g) c += p->grp[g].C;
+  return c;
+}
+
+// the tile kernels keep one in-plane offset per piece / pixel: every group must use the same row strides
+static bool tile_dirs_ok(const fwb_problem* p) {  // in-plane offsets of flow / gate / blend are 32-bit in the tile kernels
+  for (int d = 0; d < p->n_dirs; ++d) {
+    const fwb_dir& D = p->dir[d];
+    const long long m = 2147483647LL, h = p->H + 1;
+    if (D.flow_sh < 0 || D.flow_sh * h >= m) return false;
+    if (D.gate && (D.gate_sh < 0 || D.gate_sh * h >= m)) return false;
+    if (D.blend && (D.blend_sh < 0 || D.blend_sh * h >= m)) return false;
+  }
+  return true;
+}
+static bool tile_fwd_ok(const fwb_problem* p) {
+  if (total_channels(p) > TL_MAXCH || !tile_dirs_ok(p)) return false;
+  for (int g = 1; g < p->n_groups; ++g) {
+    if (p->grp[g].out_sh != p->grp[0].out_sh) return false;
+    for (int d = 0; d < p->n_dirs; ++d)
+      if (p->grp[g].src_sh[d] != p->grp[0].src_sh[d]) return false;
+  }
+  return (long long)(p->H + 1) * p->grp[0].out_sh < 2147483647LL;
+}
+static bool tile_bwd_ok(const fwb_problem* p, const fwb_grads* q) {
+  int g0 = -1, C = 0;
+  for (int g = 0; g < p->n_groups; ++g) {
+    if (!q->grad_out[g]) continue;
+    if (g0 < 0) g0 = g;
+    C += p->grp[g].C;
+    if (q->go_sh[g] != q->go_sh[g0]) return false;
+    for (int d = 0; d < p->n_dirs; ++d) {
+      if (p->grp[g].src_sh[d] != p->grp[g0].src_sh[d]) return false;
+      if (q->grad_src[g][d] && q->gs_sh[g][d] != q->gs_sh[g0][d]) return false;
+      if (q->grad_src[g][d] && !q->grad_src[g0][d]) return false;  // gs_sh[g0][d] must be meaningful
+    }
+  }
+  if (g0 < 0 || C > TL_MAXCH || !tile_dirs_ok(p)) return false;
+  for (int d = 0; d < p->n_dirs; ++d)
+    if ((long long)(p->H + 1) * q->gs_sh[g0][d] >= 2147483647LL) return false;
+  return (long long)(p->H + 1) * q->go_sh[g0] < 2147483647LL;
 }
 
 template <typename K>
@@ -472,6 +520,29 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   Params P;
   to_params(p, P);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!(knobs() & (KN_PAIRFWD | KN_NOTILE)) && stage_ok(p) && tile_fwd_ok(p)) {
+    const int sb = env_int("FWB_TILE_FWD_KB", 52) * 1024;
+    const int Ctot = total_channels(p);
+    const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + TL_TH - 1) / TL_TH, p->N * p->T);
+#define FWB_LAUNCH_TFWD(D, A, B)                                                     \
+  do {                                                                               \
+    if ((rc = set_smem(fwd_tile_kernel<D, A, B>, sb))) return rc;                    \
+    fwd_tile_kernel<D, A, B><<<grid, TL_THREADS, sb, s>>>(P, sb / 4, Ctot);          \
+  } while (0)
+    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+    switch (key) {
+      case 0: FWB_LAUNCH_TFWD(1, false, false); break;
+      case 1: FWB_LAUNCH_TFWD(1, false, true); break;
+      case 2: FWB_LAUNCH_TFWD(1, true, false); break;
+      case 3: FWB_LAUNCH_TFWD(1, true, true); break;
+      case 4: FWB_LAUNCH_TFWD(2, false, false); break;
+      case 5: FWB_LAUNCH_TFWD(2, false, true); break;
+      case 6: FWB_LAUNCH_TFWD(2, true, false); break;
+      default: FWB_LAUNCH_TFWD(2, true, true); break;
+    }
+#undef FWB_LAUNCH_TFWD
+    return (int32_t)cudaGetLastError();
+  }
   if ((knobs() & KN_PAIRFWD) && stage_ok(p)) {
     const int sb = stage_smem_bytes();
 #define FWB_LAUNCH_FWD(D, A, B)                                                      \
@@ -548,10 +619,38 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
           float* gs = Q.grad_src[gi][d];
           if (!gs) continue;
           const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
+          const long long C = p->grp[gi].C, HW = (long long)p->H * p->W;
+          if (Q.gs_sh[gi][d] == p->W && Q.gs_sc[gi][d] == HW && (Tn == 1 || Q.gs_st[gi][d] == C * HW) &&
+              (p->N == 1 || Q.gs_sn[gi][d] == Tn * C * HW)) {  // contiguous: one memset at copy-engine-free full write bandwidth
+            if ((rc = (int32_t)cudaMemsetAsync(gs, 0, (size_t)(p->N * Tn * C * HW) * sizeof(float), s))) return rc;
+            continue;
+          }
           const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
           zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d], p->N, Tn,
                                               p->grp[gi].C, p->H, p->W);
         }
+      if (!(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g)) {
+        const int sb = env_int("FWB_TILE_BWD_KB", 80) * 1024;
+        const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + TL_TH - 1) / TL_TH, p->N * p->T);
+#define FWB_LAUNCH_TBWD(D, A, B)                                                      \
+  do {                                                                                \
+    if ((rc = set_smem(bwd_tile_kernel<D, A, B>, sb))) return rc;                     \
+    bwd_tile_kernel<D, A, B><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);              \
+  } while (0)
+        const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+        switch (key) {
+          case 0: FWB_LAUNCH_TBWD(1, false, false); break;
+          case 1: FWB_LAUNCH_TBWD(1, false, true); break;
+          case 2: FWB_LAUNCH_TBWD(1, true, false); break;
+          case 3: FWB_LAUNCH_TBWD(1, true, true); break;
+          case 4: FWB_LAUNCH_TBWD(2, false, false); break;
+          case 5: FWB_LAUNCH_TBWD(2, false, true); break;
+          case 6: FWB_LAUNCH_TBWD(2, true, false); break;
+          default: FWB_LAUNCH_TBWD(2, true, true); break;
+        }
+#undef FWB_LAUNCH_TBWD
+        return (int32_t)cudaGetLastError();
+      }
       const int sb = env_int("FWB_FUSED_KB", 100) * 1024;
 #define FWB_LAUNCH_FUSED(D, A, B)                                                        \
   do {                                                                                   \

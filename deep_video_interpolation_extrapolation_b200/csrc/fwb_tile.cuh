@@ -1,0 +1,781 @@
+// fwb_tile.cuh — the default kernels: forward (kernel 1) and fused backward (kernels 2+3) on PLANAR
+// shared-memory tiles, one channel plane per pipeline stage.
+//
+// A CTA owns a 32x16 tile of output pixels of one (n, t): 8 warps, warp w owns rows w and w+8, lane = column.
+// The prologue computes everything that does not depend on the channel — taps, bilinear weights, the tile's
+// row-segment footprint (fwb_stage.cuh) for both directions, which 16-byte pieces of that footprint each
+// thread copies, the offsets of each pixel's taps inside the staged footprint — and keeps it in registers.
+// The channel loop is then a cp.async ring (TL_FD / TL_BD stages, ONE __syncthreads per channel):
+//     wait own copies of channel c | barrier | issue copies of channel c+D-1 | gather channel c from smem
+// Per (pixel, direction, channel) the forward costs 4 LDS.32 + 4 FFMA; the footprint pieces outside the image are
+// zero-filled by cp.async (src-size 0), so the gather needs no validity test: an out-of-image tap reads 0.
+// The backward adds, per channel, the scatter of grad_out*weight into an int32 FIXED-POINT shared-memory copy
+// of the same footprint (ATOMS.ADD is native, fp32 shared atomics are CAS loops on sm_100), double buffered so
+// that the flush of channel c-1 (int -> float, red.global.add.v4.f32 on the pieces the thread owns) overlaps
+// the scatter of channel c.  Scale per channel: 2^(20 - exponent(max |grad_out*blend| over the tile)).
+// Pixels whose taps are far from the rest of the tile (border-clamped outliers) are SLOW: served from global
+// memory.  A tile whose footprint does not fit goes to the generic per-pixel path.
+#pragma once
+#include "fwb_coords.cuh"
+#include "fwb_generic.cuh"
+#include "fwb_stage.cuh"
+#include "fwb_pair.cuh"
+
+namespace fwb {
+
+constexpr int TL_TW = 32, TL_TH = 16;
+constexpr int TL_THREADS = 256;
+constexpr int TL_PPT = 2;       // pixels per thread
+constexpr int TL_SLOTS = 3;     // 16-byte pieces per thread and channel (both directions together): <= 768 pieces
+constexpr int TL_MAXCH = 64;    // flattened channels per launch (table in shared memory)
+constexpr int TL_MAXSLOW = 32;  // slow pixels a tile may have before the whole tile goes generic
+constexpr int TL_FD = 4;        // forward ring depth
+constexpr int TL_BD = 4;        // backward ring depth
+
+constexpr int TL_R = 24;                       // a pixel displaced farther than this from the tile's anchor is SLOW
+constexpr int TL_ROWS = TL_TH + 2 * TL_R + 2;  // 66 source rows an inlier tap can touch: window [i0 + ady - R, ...)
+constexpr int TL_ROWS_P = 96;                  // padded: 3 rows per lane in the scan
+constexpr int TL_ZPAD = 16;                    // zero cells in front of every stage (target of tap-less pixels)
+constexpr int TL_SK4 = 3;                      // row skew in pieces: cell (x, row r) sits at offset == x + 12 r (mod 32)
+constexpr int TL_AL4 = 8;                      // row placement period in 4-cell pieces: a staged cell of image column x sits at cell offset == x (mod 16)
+
+struct TilePix {  // per (pixel of this thread, direction)
+  float tx, ty, ux, uy, bl;
+  int o0, o1;  // float offsets inside a stage of the nw and sw taps
+};
+
+// Row-segment table of one direction.  Row r is source row ybase + r.  The segment of row r, 4-aligned columns
+// [rowx, rowx + 4*len4), is stored at float offset rowbase[r] of a stage with rowbase[r] == rowx[r] (mod 32):
+// the shared-memory bank of a staged cell is its image column mod 32, so the 32 taps of a warp instruction
+// (32 consecutive output columns -> nearly consecutive source columns, whatever rows they fall on) are
+// bank-conflict free unless the flow stretches the row beyond 32 columns or folds it.
+struct TileTab {
+  int xlo[TL_ROWS_P], xhi[TL_ROWS_P];
+  int rowx[TL_ROWS_P];
+  int rowbase[TL_ROWS_P];
+  int rowoff4[129];  // exclusive prefix of the piece counts; entries above TL_ROWS_P hold INT_MAX (binary search)
+  unsigned akey32;
+  int pad0;
+  int total4;   // 16-byte pieces of this direction
+  int alloc4;   // float4 allocated (padding included), multiple of 8
+  int ybase;
+  int pad;
+};
+
+template <int NDIRS>
+struct TileCtx {
+  int n, t, j;
+  int irow[TL_PPT];
+  bool inimg[TL_PPT], act[TL_PPT];
+  TilePix px[TL_PPT][NDIRS];
+  unsigned info[TL_SLOTS];  // piece tid + s*256: dir << 31 | y << 16 | zero-fill << 15 | col
+  int pdst[TL_SLOTS];       // float offset of that piece inside a stage
+  int total;                // pieces per channel, both directions
+  int stage_f;              // floats per stage (zero pad + both directions' slots)
+  int ok;
+};
+
+__device__ __forceinline__ int piece_dir(unsigned info) { return (int)(info >> 31); }
+__device__ __forceinline__ int piece_y(unsigned info) { return (int)((info >> 16) & 0x7fffu); }
+__device__ __forceinline__ int piece_col(unsigned info) { return (int)(info & 0x7fffu); }
+__device__ __forceinline__ bool piece_zero(unsigned info) { return (info & 0x8000u) != 0u; }
+
+// one warp per direction: segment lengths, placement, prefix sums.  A pixel recorded [x0, x0+1] on its nw row only;
+// its sw / se taps are the same columns one row down, so the segment of row r is own[r] U own[r-1].
+__device__ __forceinline__ void tile_tab_scan(TileTab& tb, int slot_start4) {
+  const int lane = threadIdx.x & 31;
+  int xs[3], ln[3], ph[3];
+  int olo[3], ohi[3];
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    olo[h] = tb.xlo[3 * lane + h];
+    ohi[h] = tb.xhi[3 * lane + h];
+  }
+  int plo = __shfl_up_sync(0xffffffffu, olo[2], 1), phi = __shfl_up_sync(0xffffffffu, ohi[2], 1);
+  if (lane == 0) plo = 0x7fffffff, phi = -0x7fffffff;
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int lo = min(olo[h], h == 0 ? plo : olo[h - 1]), hi = max(ohi[h], h == 0 ? phi : ohi[h - 1]);
+    const bool has = lo <= hi;
+    xs[h] = has ? ((lo >> 2) << 2) : 0;             // arithmetic shift: -1 -> -4
+    ln[h] = has ? ((hi + 4) >> 2) - (lo >> 2) : 0;  // float4 pieces
+    ph[h] = ((xs[h] >> 2) + TL_SK4 * (3 * lane + h)) & (TL_AL4 - 1);
+  }
+  // end phase of the last non-empty row before this lane's rows (empty rows take no space and no padding):
+  // v = 8 | end phase of the lane's last non-empty row, 0 when all three are empty; inclusive "last valid" scan
+  int v_e = 0;
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+    if (ln[h] > 0) v_e = 8 | ((ph[h] + ln[h]) & (TL_AL4 - 1));
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v_e, o);
+    if (lane >= o && v_e == 0) v_e = u;
+  }
+  int e_prev = __shfl_up_sync(0xffffffffu, v_e, 1);
+  e_prev = lane == 0 ? 0 : (e_prev & 7);  // nothing before: the slot starts aligned
+  int pad[3];
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    pad[h] = ln[h] > 0 ? ((ph[h] - e_prev) & (TL_AL4 - 1)) : 0;
+    if (ln[h] > 0) e_prev = (ph[h] + ln[h]) & (TL_AL4 - 1);
+  }
+  const int mine = ((pad[0] + pad[1] + pad[2] + ln[0] + ln[1] + ln[2]) << 16) | (ln[0] + ln[1] + ln[2]);
+  int v = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
+  }
+  int run = v - mine;  // exclusive: alloc << 16 | pieces
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int r = 3 * lane + h;
+    tb.rowoff4[r] = run & 0xffff;
+    tb.rowx[r] = xs[h];
+    tb.rowbase[r] = TL_ZPAD + 4 * (slot_start4 + (run >> 16) + pad[h]);
+    run += ((pad[h] + ln[h]) << 16) | ln[h];
+  }
+  tb.rowoff4[TL_ROWS_P + lane] = 0x7fffffff;
+  if (lane == 31) {
+    tb.rowoff4[128] = 0x7fffffff;
+    tb.total4 = run & 0xffff;
+    tb.alloc4 = ((run >> 16) + TL_AL4 - 1) & ~(TL_AL4 - 1);
+  }
+}
+
+// Everything channel independent.  `tb` (NDIRS tables) lives in the dynamic shared memory that the stages
+// overwrite later: the caller must __syncthreads() between this call and the first copy.
+// The slow pixels' taps are written to slowtap from the fast taps (enough for the forward).
+// Host-checked: the in-plane offsets of flow / gate / blend fit in 32 bits.
+template <int NDIRS, bool ALIGN, bool BORDER>
+__device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, StageSlow& slow, Tap (*slowtap)[NDIRS],
+                                              int budget_floats, int stages_needed, TileCtx<NDIRS>& cx) {
+  const Geo& G = P.geo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cx.j = blockIdx.x * TL_TW + (warp & 3) * 8 + (lane & 7);  // a warp covers an 8x4 patch (fewer bank conflicts than 32x1)
+  if (G.T == 1) {
+    cx.n = blockIdx.z;
+    cx.t = 0;
+  } else {
+    cx.n = blockIdx.z / G.T;
+    cx.t = blockIdx.z - cx.n * G.T;
+  }
+  const int i0 = blockIdx.y * TL_TH;
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) {
+    cx.irow[q] = i0 + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
+    cx.inimg[q] = cx.j < G.W && cx.irow[q] < G.H;
+  }
+  int x0[TL_PPT][NDIRS], y0[TL_PPT][NDIRS];
+  unsigned vld[TL_PPT][NDIRS];
+  if (threadIdx.x < NDIRS * TL_ROWS_P) {
+    TileTab& T = tb[threadIdx.x >= TL_ROWS_P ? 1 : 0];
+    const int r = threadIdx.x >= TL_ROWS_P ? threadIdx.x - TL_ROWS_P : threadIdx.x;
+    T.xlo[r] = 0x7fffffff;
+    T.xhi[r] = -0x7fffffff;
+  }
+  if (threadIdx.x < NDIRS) tb[threadIdx.x].akey32 = 0xffffffffu;
+  if (threadIdx.x == 0) slow.n = 0;
+  __syncthreads();
+  const float bx = base_coord(cx.j, G.W, G.stepx);
+  float by[TL_PPT];
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) by[q] = base_coord(cx.irow[q], G.H, G.stepy);
+  const float fW = (float)G.W, fW1 = (float)(G.W - 1), fH = (float)G.H, fH1 = (float)(G.H - 1);
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const DirP& D = P.dir[d];
+    const DirAt at = dir_at(D, cx.n, cx.t);
+    const float* fyp = at.flow + D.flow_sc;
+    const int fsh = (int)D.flow_sh, gsh = (int)D.gate_sh, bsh = (int)D.blend_sh;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+      TilePix& px = cx.px[q][d];
+      px.tx = px.ty = px.ux = px.uy = px.bl = 0.f;
+      x0[q][d] = y0[q][d] = 0;
+      vld[q][d] = 0u;
+      if (cx.inimg[q]) {
+        const int i = cx.irow[q];
+        const int of = i * fsh + cx.j;
+        float fx = __ldg(at.flow + of), fy = __ldg(fyp + of);
+        if (at.gate) {
+          const float gate = __ldg(at.gate + (i * gsh + cx.j));
+          fx = __fmul_rn(fx, gate);
+          fy = __fmul_rn(fy, gate);
+        }
+        px.bl = at.blend ? __ldg(at.blend + (i * bsh + cx.j)) : 1.0f;
+        // bx -/+ f as one fma: sign * f is exact, so this is the same single rounding as __fsub_rn / __fadd_rn
+        const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by[q]);
+        const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1);
+        const float iy = source_index_fast<ALIGN, BORDER>(gy, fH, fH1);
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int X = (int)fx0, Y = (int)fy0;
+        px.tx = __fsub_rn(ix, fx0);
+        px.ty = __fsub_rn(iy, fy0);
+        px.ux = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+        px.uy = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
+        const bool xin0 = (unsigned)X < (unsigned)G.W, xin1 = (unsigned)(X + 1) < (unsigned)G.W;
+        const bool yin0 = (unsigned)Y < (unsigned)G.H, yin1 = (unsigned)(Y + 1) < (unsigned)G.H;
+        vld[q][d] = (unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
+                    ((unsigned)(xin1 && yin1) << 3);
+        x0[q][d] = X;
+        y0[q][d] = Y;
+      }
+      // anchor vote: the displacement (x0 - j, y0 - i) of the tile's least displaced pixel, as one 32-bit key
+      // |dx|+|dy| (10 bits) | dx (11 bits) | dy (11 bits); beyond +-1023 the anchor is clamped (the tile then goes slow / generic)
+      const int dx = min(max(x0[q][d] - cx.j, -1024), 1023), dy = min(max(y0[q][d] - cx.irow[q], -1024), 1023);
+      const unsigned mag = (unsigned)min(abs(dx) + abs(dy), 1023);
+      const unsigned key = vld[q][d] ? ((mag << 22) | (((unsigned)dx & 0x7ffu) << 11) | ((unsigned)dy & 0x7ffu)) : 0xffffffffu;
+      const unsigned best = __reduce_min_sync(0xffffffffu, key);
+      if (lane == 0 && best != 0xffffffffu) atomicMin(&tb[d].akey32, best);
+    }
+  }
+  __syncthreads();
+  int adx[NDIRS], ady[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const unsigned k = tb[d].akey32;  // ~0 when no pixel of the tile has a tap: adx = ady = -1, nobody is tested
+    adx[d] = ((int)(k << 10)) >> 21;
+    ady[d] = ((int)(k << 21)) >> 21;
+  }
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) {
+    bool far = false;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d)
+      far |= vld[q][d] != 0u && (abs(x0[q][d] - cx.j - adx[d]) > TL_R || abs(y0[q][d] - cx.irow[q] - ady[d]) > TL_R);
+    cx.act[q] = cx.inimg[q] && !far;
+    if (far) {
+      const int slot = atomicAdd(&slow.n, 1);
+      if (slot < TL_MAXSLOW) {
+        slow.pix[slot] = (unsigned short)(((cx.irow[q] - i0) << 5) | (cx.j - blockIdx.x * TL_TW));
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          Tap& k = slowtap[slot][d];
+          k.x0 = x0[q][d];
+          k.y0 = y0[q][d];
+          k.valid = vld[q][d];
+          k.tx = cx.px[q][d].tx;
+          k.ty = cx.px[q][d].ty;
+          k.ux = cx.px[q][d].ux;
+          k.uy = cx.px[q][d].uy;
+          k.blend = cx.px[q][d].bl;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      if (!cx.act[q]) vld[q][d] = 0u;
+      if (vld[q][d]) {
+        TileTab& T = tb[d];
+        const int r = y0[q][d] - (i0 + ady[d] - TL_R);  // 0 .. TL_ROWS - 3
+        atomicMin(&T.xlo[r], x0[q][d]);
+        atomicMax(&T.xhi[r], x0[q][d] + 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp < NDIRS) tile_tab_scan(tb[warp], 0);
+  __syncthreads();
+  cx.ok = slow.n <= TL_MAXSLOW;
+  const int tot0 = tb[0].total4;
+  cx.total = tot0;
+  int alloc = tb[0].alloc4;
+  if (NDIRS > 1) {
+    cx.total += tb[NDIRS - 1].total4;
+    alloc += tb[NDIRS - 1].alloc4;
+  }
+  cx.stage_f = TL_ZPAD + 4 * alloc;
+  if (cx.total > TL_SLOTS * TL_THREADS || stages_needed * cx.stage_f > budget_floats) cx.ok = 0;
+  if (!cx.ok) return;
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const TileTab& T = tb[d];
+    const int yb = i0 + ady[d] - TL_R;
+    const int doff = d == 0 ? 0 : 4 * tb[0].alloc4;  // the second direction's slot follows the first one's
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+      cx.px[q][d].o0 = cx.px[q][d].o1 = 0;
+      if (vld[q][d]) {
+        const int r = y0[q][d] - yb;
+        cx.px[q][d].o0 = doff + T.rowbase[r] + (x0[q][d] - T.rowx[r]);
+        cx.px[q][d].o1 = doff + T.rowbase[r + 1] + (x0[q][d] - T.rowx[r + 1]);
+      }
+    }
+  }
+  // which pieces this thread copies: piece k = tid + s*256 of the two directions' piece lists back to back
+#pragma unroll
+  for (int s = 0; s < TL_SLOTS; ++s) {
+    const int k = threadIdx.x + s * TL_THREADS;
+    cx.info[s] = 0x8000u;
+    cx.pdst[s] = 0;
+    if (k < cx.total) {
+      const int d = (NDIRS > 1 && k >= tot0) ? 1 : 0;
+      const TileTab& T = tb[d];
+      const int kk = k - (d ? tot0 : 0);
+      int r = 0;  // last row with rowoff4[r] <= kk
+#pragma unroll
+      for (int step = 64; step > 0; step >>= 1)
+        if (T.rowoff4[r + step] <= kk) r += step;
+      const int e = kk - T.rowoff4[r];
+      const int y = i0 + ady[d] - TL_R + r, col = T.rowx[r] + 4 * e;
+      const bool in = y >= 0 && y < G.H && col >= 0 && col < G.W;  // W % 4 == 0: a piece is all in or all out
+      cx.info[s] = ((unsigned)d << 31) | (in ? (((unsigned)y << 16) | (unsigned)col) : 0x8000u);
+      cx.pdst[s] = (d ? 4 * tb[0].alloc4 : 0) + T.rowbase[r] + 4 * e;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers: 32-bit shared addresses, predicated copies / stores (no branches in the channel loop)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tl_lds(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float tl_lds4(unsigned a) {  // [a + 4]
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long tl_lds64(unsigned a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+// 16-byte async copy, issued only when `on`; `bytes` (0 or 16) come from memory, the rest is zero-filled
+__device__ __forceinline__ void cp_async16_if(unsigned dst, const void* src, int bytes, bool on) {
+  asm volatile(
+      "{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp cp.async.cg.shared.global [%0], [%1], 16, %2;\n}\n" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"((int)on)
+      : "memory");
+}
+__device__ __forceinline__ void red_shared_add(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_shared_add_4(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0+4], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Per-thread copy plan of one channel: element offset inside a plane of each piece (or a flag)
+constexpr int PIECE_ZERO = -1, PIECE_NONE = -2;
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: fused forward warp (+gate) (+blend), NDIRS directions, all channel groups.
+// All groups share the row strides (host-checked), so a piece's offset inside a plane is channel independent.
+// ---------------------------------------------------------------------------------------------
+struct TileChanF {
+  const float* src[2];
+  float* out;
+  long long pad;
+};
+
+template <int NDIRS, bool ALIGN, bool BORDER>
+__global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_constant__ Params P, int smem_floats, int Ctot) {
+  extern __shared__ float4 tl_smem4[];
+  float* const smem = reinterpret_cast<float*>(tl_smem4);
+  __shared__ StageSlow slow;
+  __shared__ Tap slowtap[TL_MAXSLOW][NDIRS];
+  __shared__ __align__(16) TileChanF tab[TL_MAXCH];
+  int n, t, j, stage_f;
+  bool act[TL_PPT];
+  float w[TL_PPT][NDIRS][4], bl[TL_PPT][NDIRS];
+  unsigned a0[TL_PPT][NDIRS], a1[TL_PPT][NDIRS];  // shared byte addresses (stage 0) of the nw and sw taps
+  int poff[TL_SLOTS];                             // piece tid + s*256: element offset in its plane / PIECE_*
+  unsigned tsel[TL_SLOTS];                        // byte offset of the piece's direction inside a table entry
+  unsigned pd[TL_SLOTS];                          // shared byte address (stage 0) the piece is copied to
+  int ooff[TL_PPT];
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+  {
+    TileCtx<NDIRS> cx;
+    tile_prologue<NDIRS, ALIGN, BORDER>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_FD, cx);
+    n = cx.n, t = cx.t, j = cx.j;
+    if (!cx.ok) {  // wild flow: the tile's source footprint does not fit -> gather from global memory
+#pragma unroll
+      for (int q = 0; q < TL_PPT; ++q)
+        if (cx.inimg[q]) fwd_generic_pixel<NDIRS>(P, n, t, cx.irow[q], j);
+      return;
+    }
+    stage_f = cx.stage_f;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+      act[q] = cx.act[q];
+      ooff[q] = cx.irow[q] * P.grp[0].out_sh + j;
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const TilePix& px = cx.px[q][d];
+        w[q][d][0] = __fmul_rn(px.ux, px.uy);
+        w[q][d][1] = __fmul_rn(px.tx, px.uy);
+        w[q][d][2] = __fmul_rn(px.ux, px.ty);
+        w[q][d][3] = __fmul_rn(px.tx, px.ty);
+        bl[q][d] = px.bl;
+        a0[q][d] = smem_s + 4u * (unsigned)px.o0;
+        a1[q][d] = smem_s + 4u * (unsigned)px.o1;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < TL_SLOTS; ++s) {
+      const unsigned info = cx.info[s];
+      const int d = piece_dir(info);
+      tsel[s] = 8u * (unsigned)d;
+      pd[s] = smem_s + 4u * (unsigned)cx.pdst[s];
+      poff[s] = threadIdx.x + s * TL_THREADS >= cx.total ? PIECE_NONE
+                : piece_zero(info)                       ? PIECE_ZERO
+                                                         : piece_y(info) * P.grp[0].src_sh[d] + piece_col(info);
+    }
+  }
+  if (threadIdx.x < Ctot) {
+    int g, c;
+    chan_lookup(P, threadIdx.x, g, c);
+    const GroupP& R = P.grp[g];
+    TileChanF e;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) e.src[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d];
+    e.out = R.out + n * R.out_sn + t * R.out_st + (long long)c * R.out_sc;
+    e.pad = 0;
+    tab[threadIdx.x] = e;
+  }
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) has_bl[d] = P.dir[d].blend != nullptr;
+  __syncthreads();  // the tables in dynamic shared memory are dead from here on; tab / slowtap are visible
+  if (threadIdx.x < TL_FD * TL_ZPAD) smem[(threadIdx.x / TL_ZPAD) * stage_f + (threadIdx.x % TL_ZPAD)] = 0.f;
+  const unsigned stage_b = 4u * (unsigned)stage_f;
+  const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+
+  auto issue = [&](int cf, unsigned soff) {  // copies of channel cf into the stage at byte offset soff
+    const bool live = cf < Ctot;
+    const unsigned te = tab_s + (unsigned)sizeof(TileChanF) * (unsigned)(live ? cf : 0);
+#pragma unroll
+    for (int s = 0; s < TL_SLOTS; ++s) {
+      const float* base = reinterpret_cast<const float*>(tl_lds64(te + tsel[s]));
+      cp_async16_if(pd[s] + soff, base + max(poff[s], 0), poff[s] >= 0 ? 16 : 0, live && poff[s] != PIECE_NONE);
+    }
+    cp_async_commit();
+  };
+  {
+    unsigned so = 0;
+#pragma unroll
+    for (int p = 0; p < TL_FD - 1; ++p, so += stage_b) issue(p, so);
+  }
+  // slow pixels, while the first copies are in flight: one (pixel, channel) item per thread
+  for (int it = threadIdx.x; it < slow.n * Ctot; it += TL_THREADS) {
+    const int sidx = it / Ctot, pix = slow.pix[sidx];
+    fwd_slow_item<NDIRS>(P, n, t, blockIdx.y * TL_TH + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx], it - sidx * Ctot);
+  }
+  unsigned soff = 0, poffs = (TL_FD - 1) * stage_b;  // stage of channel cf; stage the copies of channel cf+D-1 go to
+  const unsigned ring_b = TL_FD * stage_b;
+  unsigned te = tab_s + 16u;  // &tab[cf].out
+#pragma unroll 1
+  for (int cf = 0; cf < Ctot; ++cf) {
+    cp_async_wait<TL_FD - 2>();
+    __syncthreads();  // channel cf has landed for every thread; everyone is done with channel cf-1
+    issue(cf + TL_FD - 1, poffs);
+    float* const op = reinterpret_cast<float*>(tl_lds64(te));
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+      float r = 0.f;
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const unsigned s0 = a0[q][d] + soff, s1 = a1[q][d] + soff;
+        float a = __fmul_rn(tl_lds(s0), w[q][d][0]);
+        a = __fmaf_rn(tl_lds4(s0), w[q][d][1], a);
+        a = __fmaf_rn(tl_lds(s1), w[q][d][2], a);
+        a = __fmaf_rn(tl_lds4(s1), w[q][d][3], a);
+        if (has_bl[d]) a = __fmul_rn(a, bl[q][d]);
+        r = (d == 0) ? a : __fadd_rn(r, a);
+      }
+      st_cs_if(op + ooff[q], r, act[q]);
+    }
+    soff += stage_b;
+    if (soff == ring_b) soff = 0;
+    poffs += stage_b;
+    if (poffs == ring_b) poffs = 0;
+    te += (unsigned)sizeof(TileChanF);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernels 2 + 3 fused (non-deterministic fast backward).  Row strides shared by all groups (host-checked).
+// ---------------------------------------------------------------------------------------------
+struct TileChanB {
+  const float* src[2];
+  float* gs[2];  // may be NULL
+  const float* go;
+  int g, c;  // group / channel (the non-finite path needs them)
+};
+
+// inf / NaN in grad_out of this channel: exact float atomics straight to global memory (rare path, kept out of line)
+__device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, int n, int t, int i, int j, int g, int c, int d, float gw) {
+  Tap k;
+  compute_tap(P.geo, P.dir[d], n, t, i, j, k);
+  scatter_atomic_px(Q, g, d, n, t, c, false, k, gw, 0.f);
+}
+
+template <int NDIRS, bool ALIGN, bool BORDER>
+__global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+                                                                 int smem_floats) {
+  extern __shared__ float4 tl_smem4[];
+  float* const smem = reinterpret_cast<float*>(tl_smem4);
+  __shared__ StageSlow slow;
+  __shared__ Tap slowtap[TL_MAXSLOW][NDIRS];
+  __shared__ __align__(16) TileChanB tab[TL_MAXCH];
+  __shared__ unsigned amax_s[3];
+  __shared__ int nchan_s, g0_s;
+  const Geo& G = P.geo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int n, t, j, total, stage_f;
+  int irow[TL_PPT];
+  bool act[TL_PPT];
+  float tx[TL_PPT][NDIRS], ty[TL_PPT][NDIRS], ux[TL_PPT][NDIRS], uy[TL_PPT][NDIRS], bl[TL_PPT][NDIRS];
+  unsigned a0[TL_PPT][NDIRS], a1[TL_PPT][NDIRS];  // byte offsets inside a stage of the nw and sw taps
+  unsigned info[TL_SLOTS];
+  unsigned pd[TL_SLOTS];  // byte offset inside a stage of piece tid + s*256
+  {
+    TileCtx<NDIRS> cx;
+    tile_prologue<NDIRS, ALIGN, BORDER>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
+    n = cx.n, t = cx.t, j = cx.j;
+    if (!cx.ok) {
+#pragma unroll
+      for (int q = 0; q < TL_PPT; ++q)
+        if (cx.inimg[q]) bwd_fused_generic_pixel<NDIRS>(P, Q, n, t, cx.irow[q], j);
+      return;
+    }
+    total = cx.total;
+    stage_f = cx.stage_f;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+      irow[q] = cx.irow[q];
+      act[q] = cx.act[q];
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const TilePix& px = cx.px[q][d];
+        tx[q][d] = px.tx, ty[q][d] = px.ty, ux[q][d] = px.ux, uy[q][d] = px.uy, bl[q][d] = px.bl;
+        a0[q][d] = 4u * (unsigned)px.o0;
+        a1[q][d] = 4u * (unsigned)px.o1;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < TL_SLOTS; ++s) {
+      info[s] = cx.info[s];
+      pd[s] = 4u * (unsigned)cx.pdst[s];
+    }
+  }
+  // channel table over the groups that have a grad_out (the others contribute nothing)
+  if (threadIdx.x < 32) {
+    int base = 0, g0 = -1;
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      if (g0 < 0) g0 = g;
+      const GroupP& R = P.grp[g];
+      for (int c = lane; c < R.C; c += 32) {
+        TileChanB e;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          e.src[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d];
+          float* gs = (d < NDIRS) ? Q.grad_src[g][d] : nullptr;
+          e.gs[d] = gs ? gs + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d] : nullptr;
+        }
+        e.go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)c * Q.go_sc[g];
+        e.g = g;
+        e.c = c;
+        tab[base + c] = e;
+      }
+      base += R.C;
+    }
+    if (lane == 0) {
+      nchan_s = base;
+      g0_s = g0 < 0 ? 0 : g0;
+    }
+  }
+  if (threadIdx.x < 3) amax_s[threadIdx.x] = 0u;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + slow.n) {  // the slow path of the backward needs the full taps (multipliers, raw flow)
+    const int sidx = threadIdx.x - 32, pix = slow.pix[sidx];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) compute_tap(G, P.dir[d], n, t, blockIdx.y * TL_TH + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d]);
+  }
+  bool has_bl[NDIRS];
+  float blmax[TL_PPT];
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) blmax[q] = 0.f;
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    has_bl[d] = P.dir[d].blend != nullptr;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) blmax[q] = fmaxf(blmax[q], has_bl[d] ? fabsf(bl[q][d]) : 1.0f);
+  }
+  float gix[TL_PPT][NDIRS], giy[TL_PPT][NDIRS], gbl[TL_PPT][NDIRS];
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q)
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) gix[q][d] = giy[q][d] = gbl[q][d] = 0.f;
+  __syncthreads();  // the tables in dynamic shared memory are dead from here on; tab / slowtap / amax_s are visible
+  const int Cn = nchan_s, g0 = g0_s;
+  // per-thread copy / flush plan (row strides are those of group g0: all groups agree)
+  int poff[TL_SLOTS], goff[TL_SLOTS];  // element offset of piece tid + s*256 in its src plane / grad_src plane, or PIECE_*
+  unsigned tsel[TL_SLOTS];
+#pragma unroll
+  for (int s = 0; s < TL_SLOTS; ++s) {
+    const int d = piece_dir(info[s]);
+    tsel[s] = 8u * (unsigned)d;
+    const bool none = threadIdx.x + s * TL_THREADS >= total, zero = piece_zero(info[s]);
+    poff[s] = none ? PIECE_NONE : zero ? PIECE_ZERO : piece_y(info[s]) * P.grp[g0].src_sh[d] + piece_col(info[s]);
+    goff[s] = (none || zero) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
+  }
+  int gooff[TL_PPT];
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) gooff[q] = irow[q] * Q.go_sh[g0] + j;
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned stage_b = 4u * (unsigned)stage_f;
+  const unsigned acc_s = smem_s + TL_BD * stage_b;  // two accumulators, stage layout
+#pragma unroll
+  for (int s = 0; s < TL_SLOTS; ++s)
+    if (goff[s] >= 0) {  // the pieces this thread flushes start from zero (the rest of the accumulators is never read)
+      asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + pd[s]), "r"(0) : "memory");
+      asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + stage_b + pd[s]), "r"(0) : "memory");
+    }
+  if (threadIdx.x < TL_BD * TL_ZPAD) smem[(threadIdx.x / TL_ZPAD) * stage_f + (threadIdx.x % TL_ZPAD)] = 0.f;
+  const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+
+  auto issue = [&](int cf, unsigned soff) {
+    const bool live = cf < Cn;
+    const unsigned te = tab_s + (unsigned)sizeof(TileChanB) * (unsigned)(live ? cf : 0);
+#pragma unroll
+    for (int s = 0; s < TL_SLOTS; ++s) {
+      const float* base = reinterpret_cast<const float*>(tl_lds64(te + tsel[s]));
+      cp_async16_if(smem_s + pd[s] + soff, base + max(poff[s], 0), poff[s] >= 0 ? 16 : 0, live && poff[s] != PIECE_NONE);
+    }
+    cp_async_commit();
+  };
+  auto load_go = [&](int cf, float* go) {
+    const bool live = cf < Cn;
+    const float* gp = tab[live ? cf : 0].go;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) go[q] = (live && act[q]) ? __ldcs(gp + gooff[q]) : 0.f;
+  };
+  auto vote_amax = [&](const float* go, int slot) {
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q)  // NaN must win the max: compare the bit patterns (non-negative floats order like uints)
+      m = __uint_as_float(max(__float_as_uint(m), __float_as_uint(fabsf(go[q]) * blmax[q])));
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if (lane == 0 && mb != 0u) atomicMax(&amax_s[slot], mb);
+  };
+  // flush this thread's pieces of the accumulator at byte address `ab` (channel cf) into grad_src
+  auto flush = [&](int cf, unsigned ab, float Sinv) {
+    const unsigned te = tab_s + (unsigned)sizeof(TileChanB) * (unsigned)cf + 16u;  // &tab[cf].gs[0]
+#pragma unroll
+    for (int s = 0; s < TL_SLOTS; ++s) {
+      if (goff[s] < 0) continue;
+      const unsigned a = ab + pd[s];
+      int4 u;
+      asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a));
+      if ((u.x | u.y | u.z | u.w) == 0) continue;
+      float* gs = reinterpret_cast<float*>(tl_lds64(te + tsel[s]));
+      if (gs) red_add_v4(gs + goff[s], make_float4((float)u.x * Sinv, (float)u.y * Sinv, (float)u.z * Sinv, (float)u.w * Sinv));
+      asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0) : "memory");
+    }
+  };
+
+  {
+    unsigned so = 0;
+#pragma unroll
+    for (int p = 0; p < TL_BD - 1; ++p, so += stage_b) issue(p, so);
+  }
+  float go[TL_PPT], gn[TL_PPT];
+  load_go(0, go);
+  vote_amax(go, 0);
+  // slow pixels, while the first copies are in flight: one warp per pixel, lanes over the channels
+  for (int s = warp; s < slow.n; s += TL_THREADS / 32) {
+    const int pix = slow.pix[s];
+    const int si = blockIdx.y * TL_TH + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
+    bwdflow_slow_warp<NDIRS>(P, Q, n, t, si, sj, slowtap[s]);
+    for (int cf = lane; cf < Cn; cf += 32) {
+      const TileChanB& tc = tab[cf];
+      const float gout = __ldg(tc.go + si * Q.go_sh[g0] + sj);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d)
+        scatter_atomic_px(Q, tc.g, d, n, t, tc.c, false, slowtap[s][d], has_bl[d] ? gout * slowtap[s][d].blend : gout, 0.f);
+    }
+  }
+  constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: fma(x, y, MAGIC) holds round-to-nearest(x*y) in its low mantissa bits
+  constexpr int MAGIC_BITS = 0x4B400000;
+  unsigned soff = 0, poffs = (TL_BD - 1) * stage_b;
+  const unsigned ring_b = TL_BD * stage_b;
+  unsigned aoff = 0;  // byte offset of the accumulator of channel cf (0 / stage_b)
+  float Sinv_prev = 0.f;
+  bool flush_prev = false;
+#pragma unroll 1
+  for (int cf = 0; cf < Cn; ++cf) {
+    cp_async_wait<TL_BD - 2>();
+    __syncthreads();  // channel cf has landed; scatter of cf-1 complete; flush of cf-2 complete
+    issue(cf + TL_BD - 1, poffs);
+    load_go(cf + 1, gn);
+    if (threadIdx.x == 0) amax_s[(cf + 2) % 3] = 0u;
+    if (flush_prev) flush(cf - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
+    // ---- scale of this channel
+    const unsigned ab = amax_s[cf % 3];
+    const bool finite = ab < 0x7f800000u;
+    const int sexp = min(252, max(2, 274 - (int)(ab >> 23)));  // biased exponent of 2^(20 - exponent(amax))
+    const float S = __uint_as_float((unsigned)sexp << 23);
+    const float Sinv = __uint_as_float((unsigned)(254 - sexp) << 23);
+    const TileChanB& tc = tab[cf];
+    const unsigned sb = smem_s + soff, ac = acc_s + aoff;
+    bool want[NDIRS];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) want[d] = tc.gs[d] != nullptr;
+    const float Sf = (finite && ab != 0u) ? S : 0.f;  // 0: nothing goes to the accumulator
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) {
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const float a = tl_lds(sb + a0[q][d]), b = tl_lds4(sb + a0[q][d]);
+        const float c_ = tl_lds(sb + a1[q][d]), dd = tl_lds4(sb + a1[q][d]);
+        float gw = go[q];
+        if (has_bl[d]) {
+          const float top = fmaf(b, tx[q][d], a * ux[q][d]), bot = fmaf(dd, tx[q][d], c_ * ux[q][d]);
+          gbl[q][d] = fmaf(go[q], fmaf(bot, ty[q][d], top * uy[q][d]), gbl[q][d]);
+          gw *= bl[q][d];
+        }
+        gix[q][d] = fmaf(gw, fmaf(ty[q][d], dd - c_, uy[q][d] * (b - a)), gix[q][d]);
+        giy[q][d] = fmaf(gw, fmaf(tx[q][d], dd - b, ux[q][d] * (c_ - a)), giy[q][d]);
+        if (want[d]) {
+          const float sgw = (finite ? gw : 0.f) * Sf;
+          const float gl = sgw * ux[q][d], gr = sgw * tx[q][d];
+          red_shared_add(ac + a0[q][d], __float_as_int(fmaf(gl, uy[q][d], MAGIC)) - MAGIC_BITS);
+          red_shared_add_4(ac + a0[q][d], __float_as_int(fmaf(gr, uy[q][d], MAGIC)) - MAGIC_BITS);
+          red_shared_add(ac + a1[q][d], __float_as_int(fmaf(gl, ty[q][d], MAGIC)) - MAGIC_BITS);
+          red_shared_add_4(ac + a1[q][d], __float_as_int(fmaf(gr, ty[q][d], MAGIC)) - MAGIC_BITS);
+        }
+      }
+    }
+    if (!finite) {  // inf / NaN in this channel's grad_out (rare): float atomics straight to global memory
+      for (int q = 0; q < TL_PPT; ++q)
+        for (int d = 0; d < NDIRS; ++d)
+          if (tc.gs[d] != nullptr && act[q]) bwd_nonfinite_px(P, Q, n, t, irow[q], j, tc.g, tc.c, d, has_bl[d] ? go[q] * bl[q][d] : go[q]);
+    }
+    vote_amax(gn, (cf + 1) % 3);
+#pragma unroll
+    for (int q = 0; q < TL_PPT; ++q) go[q] = gn[q];
+    Sinv_prev = Sinv;
+    flush_prev = finite && ab != 0u;
+    soff += stage_b;
+    if (soff == ring_b) soff = 0;
+    poffs += stage_b;
+    if (poffs == ring_b) poffs = 0;
+    aoff ^= stage_b;
+  }
+  __syncthreads();
+  if (flush_prev) flush(Cn - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
+
+#pragma unroll
+  for (int q = 0; q < TL_PPT; ++q) {
+    if (!act[q]) continue;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      Tap k;
+      compute_tap(G, P.dir[d], n, t, irow[q], j, k);  // mx, my, fx, fy, gate (cheaper to recompute than to hold)
+      bwdflow_store(P, Q, d, n, t, irow[q], j, k, gix[q][d], giy[q][d], gbl[q][d]);
+    }
+  }
+}
+
+}  // namespace fwb

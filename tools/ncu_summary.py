@@ -1,27 +1,25 @@
-"""Summarise an .ncu-rep (raw page) — key metrics per kernel.  usage: ncu_summary.py file.ncu-rep [more metrics...]"""
+#!/usr/bin/env python
+"""Print the metrics that matter for this path from an .ncu-rep (ncu -i rep --page raw --csv)."""
 import csv, subprocess, sys
-WANT = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','launch__registers_per_thread','launch__occupancy_limit_registers','launch__occupancy_limit_shared_mem',
- 'sm__warps_active.avg.pct_of_peak_sustained_active','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct','lts__t_bytes.sum','smsp__inst_executed.sum',
- 'sm__throughput.avg.pct_of_peak_sustained_elapsed','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed',
- 'dram__throughput.avg.pct_of_peak_sustained_elapsed','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','smsp__issue_active.avg.pct_of_peak_sustained_active',
- 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
- 'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio','smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio','smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio','smsp__average_warps_issue_stalled_membar_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio','smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio','smsp__average_warps_issue_stalled_drain_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio','smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
- 'smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_selected_per_issue_active.ratio',
- 'sm__cycles_elapsed.max','sm__cycles_active.avg']
-rep = sys.argv[1]
-extra = sys.argv[2:]
-out = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, units = rows[0], rows[1]
+WANT = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.sum', 'sm__cycles_elapsed.max']
+rows = list(csv.reader(subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout.splitlines()))
+hdr = rows[0]
 for r in rows[2:]:
     print('==', r[hdr.index('Kernel Name')])
-    for w in WANT+extra:
-        if w in hdr:
-            i = hdr.index(w); print('  %-85s %s %s' % (w, r[i], units[i]))
+    for i, h in enumerate(hdr):
+        if h in WANT or 'issue_stalled' in h and h.endswith('per_issue_active.ratio') and 'not_issued' not in h:
+            try:
+                v = float(r[i])
+            except ValueError:
+                continue
+            if 'issue_stalled' in h and v < 0.3:
+                continue
+            print(f'  {h:90s} {r[i]} {rows[1][i]}')

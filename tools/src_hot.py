@@ -1,23 +1,21 @@
-"""per-source-line instruction counts of one kernel: usage src_hot.py rep.ncu-rep kernel_regex [topN]"""
-import csv, subprocess, sys
-rep, rx = sys.argv[1], sys.argv[2]
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass','--kernel-name','regex:'+rx],capture_output=True,text=True).stdout
-cur=None; rows=[]; seen_fn=set(); first_fn=None
-fn=None
-for r in csv.reader(out.splitlines()):
-    if len(r)>=2 and r[0]=='File Path': cur=r[1].split('/')[-1]; continue
-    if len(r)>=2 and r[0]=='Function Name':
-        fn=r[1]
-        if first_fn is None: first_fn=fn
-        continue
-    if len(r)>8 and r[0].isdigit() and fn==first_fn:
-        try: rows.append((cur,int(r[0]),r[1].strip(),int(r[7]),int(r[6])))
-        except ValueError: pass
-tot=sum(x[3] for x in rows); ts=sum(x[4] for x in rows)
-print('kernel',first_fn,'total warp instr',tot,'samples',ts)
-byfile={}
-for f,l,s,c,sm in rows: byfile[f]=byfile.get(f,0)+c
-print({k:'%.1f%%'%(100*v/tot) for k,v in byfile.items()})
-for f,l,s,c,sm in sorted(rows,key=lambda x:-x[3])[:top]:
-    print('%5.1f%% instr %5.1f%% samp  %s:%d  %s'%(100*c/tot,100*sm/max(ts,1),f,l,s[:100]))
+#!/usr/bin/env python
+"""Per-region instruction / stall-sample / shared-wavefront totals from `ncu --page source --csv` output.
+usage: src_hot.py file.csv [bucket_size_in_instructions]"""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[1]
+iA, iS, iN, iI = hdr.index('Address'), hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
+iW = hdr.index('L1 Wavefronts Shared'); iWi = hdr.index('L1 Wavefronts Shared Ideal')
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+body = [r for r in rows[2:] if len(r) > max(iI, iW, iWi) and r[iI].isdigit()]
+tot_i = sum(int(r[iI]) for r in body); tot_s = sum(int(r[iN]) for r in body)
+print('total inst', tot_i, 'samples', tot_s, 'n sass', len(body))
+for b in range(0, len(body), B):
+    ch = body[b:b + B]
+    ins = sum(int(r[iI]) for r in ch); sm = sum(int(r[iN]) for r in ch)
+    wf = sum(int(r[iW]) for r in ch); wfi = sum(int(r[iWi]) for r in ch)
+    tags = [r[iS].split()[0] if not r[iS].strip().startswith('@') else r[iS].split()[1] for r in ch]
+    marks = [t for t in tags if t.startswith(('BAR', 'LDGSTS', 'ATOMS', 'REDG', 'STG', 'LDG', 'REDUX', 'EXIT', 'ATOMG'))]
+    from collections import Counter
+    c = Counter(m.split('.')[0] for m in marks)
+    print(f'{b:5d} inst {ins/tot_i*100:5.1f}%  samples {sm/max(tot_s,1)*100:5.1f}%  wf {wf:9d} ideal {wfi:9d}  {dict(c)}')
