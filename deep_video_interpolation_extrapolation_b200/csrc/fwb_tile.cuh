@@ -41,6 +41,7 @@ constexpr int TL_AL4 = 8;                      // row placement period in 4-cell
 
 struct TilePix {  // per (pixel of this thread, direction)
   float tx, ty, ux, uy, bl;
+  unsigned clip;  // bit 0 / 1: border padding clipped ix / iy (the coordinate gradient is then zero)
   int o0, o1;  // float offsets inside a stage of the nw and sw taps
 };
 
@@ -193,6 +194,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     for (int q = 0; q < TL_PPT; ++q) {
       TilePix& px = cx.px[q][d];
       px.tx = px.ty = px.ux = px.uy = px.bl = 0.f;
+      px.clip = 0u;
       x0[q][d] = y0[q][d] = 0;
       vld[q][d] = 0u;
       if (cx.inimg[q]) {
@@ -209,6 +211,11 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
         const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by[q]);
         const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1);
         const float iy = source_index_fast<ALIGN, BORDER>(gy, fH, fH1);
+        if (BORDER) {  // clipped <=> the unclipped coordinate was <= 0 or >= size-1 (NaN: not clipped, as in source_index)
+          const float cx_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), fW1) : __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), fW, -1.0f), 0.5f);
+          const float cy_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), fH1) : __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), fH, -1.0f), 0.5f);
+          px.clip = (unsigned)(cx_ <= 0.f || cx_ >= fW1) | ((unsigned)(cy_ <= 0.f || cy_ >= fH1) << 1);
+        }
         const float fx0 = floorf(ix), fy0 = floorf(iy);
         const int X = (int)fx0, Y = (int)fy0;
         px.tx = __fsub_rn(ix, fx0);
@@ -529,6 +536,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   unsigned a0[TL_PPT][NDIRS], a1[TL_PPT][NDIRS];  // byte offsets inside a stage of the nw and sw taps
   unsigned info[TL_SLOTS];
   unsigned pd[TL_SLOTS];  // byte offset inside a stage of piece tid + s*256
+  unsigned clipbits = 0u;  // 2 bits per (q, d): the coordinate gradient is zero (border clipping)
   {
     TileCtx<NDIRS> cx;
     tile_prologue<NDIRS, ALIGN, BORDER>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
@@ -549,6 +557,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
       for (int d = 0; d < NDIRS; ++d) {
         const TilePix& px = cx.px[q][d];
         tx[q][d] = px.tx, ty[q][d] = px.ty, ux[q][d] = px.ux, uy[q][d] = px.uy, bl[q][d] = px.bl;
+        clipbits |= px.clip << (2 * (q * NDIRS + d));
         a0[q][d] = 4u * (unsigned)px.o0;
         a1[q][d] = 4u * (unsigned)px.o1;
       }
@@ -766,13 +775,29 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   __syncthreads();
   if (flush_prev) flush(Cn - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
 
+  // epilogue: coordinate gradient -> grad_flow / grad_gate / grad_blend.  The multipliers are d(ix)/d(gx) = W/2 or (W-1)/2,
+  // zero where border padding clipped the coordinate; the raw flow and the gate are reloaded only when there is a gate.
+  const float mxc = ALIGN ? __fmul_rn((float)(G.W - 1), 0.5f) : __fmul_rn((float)G.W, 0.5f);
+  const float myc = ALIGN ? __fmul_rn((float)(G.H - 1), 0.5f) : __fmul_rn((float)G.H, 0.5f);
 #pragma unroll
   for (int q = 0; q < TL_PPT; ++q) {
     if (!act[q]) continue;
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {
+      const unsigned cb = clipbits >> (2 * (q * NDIRS + d));
       Tap k;
-      compute_tap(G, P.dir[d], n, t, irow[q], j, k);  // mx, my, fx, fy, gate (cheaper to recompute than to hold)
+      k.mx = (cb & 1u) ? 0.f : mxc;
+      k.my = (cb & 2u) ? 0.f : myc;
+      k.fx = k.fy = 0.f;
+      k.gate = 1.f;
+      const DirP& D = P.dir[d];
+      if (D.gate != nullptr) {
+        const DirAt at = dir_at(D, n, t);
+        const int of = irow[q] * (int)D.flow_sh + j;
+        k.fx = __ldg(at.flow + of);
+        k.fy = __ldg(at.flow + D.flow_sc + of);
+        k.gate = __ldg(at.gate + (irow[q] * (int)D.gate_sh + j));
+      }
       bwdflow_store(P, Q, d, n, t, irow[q], j, k, gix[q][d], giy[q][d], gbl[q][d]);
     }
   }
