@@ -404,9 +404,10 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-# launches of OUR kernels per step (forward 1, backward_flow 1, backward_src: see csrc/flowwarp_b200.cu)
-# fused: forward 1 + zero grad_src 4 + fused backward 1; split: forward 1 + (table init 1 + emit 1 + kernel 2) + kernel 3 x2
-LAUNCHES_PER_STEP = {"fused": 1 + 4 + 1, "split": 1 + 3 + 2}
+# launches of OUR kernels per step (see csrc/flowwarp_b200.cu)
+# fused: fwd_tile_kernel 1 + bwd_tile_kernel 1 (grad_src is zeroed by 4 cudaMemsetAsync nodes, not counted);
+# split (deterministic): forward 1 + (table init 1 + emit 1 + kernel 2) + kernel 3 x2
+LAUNCHES_PER_STEP = {"fused": 1 + 1, "split": 1 + 3 + 2}
 
 
 def main():
