@@ -630,12 +630,18 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
                                               p->grp[gi].C, p->H, p->W);
         }
       if (!(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g)) {
-        const int sb = env_int("FWB_TILE_BWD_KB", 80) * 1024;
-        const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + TL_TH - 1) / TL_TH, p->N * p->T);
-#define FWB_LAUNCH_TBWD(D, A, B)                                                      \
-  do {                                                                                \
-    if ((rc = set_smem(bwd_tile_kernel<D, A, B>, sb))) return rc;                     \
-    bwd_tile_kernel<D, A, B><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);              \
+        const int ppt = env_int("FWB_TILE_BWD_PPT", 2);  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
+        const int sb = env_int("FWB_TILE_BWD_KB", ppt == 1 ? 48 : 80) * 1024;
+        const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);
+#define FWB_LAUNCH_TBWD(D, A, B)                                                                  \
+  do {                                                                                            \
+    if (ppt == 1) {                                                                               \
+      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 1, 2>, sb))) return rc;                         \
+      bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
+    } else {                                                                                      \
+      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3>, sb))) return rc;                         \
+      bwd_tile_kernel<D, A, B, 2, 3><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
+    }                                                                                             \
   } while (0)
         const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
         switch (key) {

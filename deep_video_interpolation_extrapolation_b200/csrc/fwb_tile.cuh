@@ -33,7 +33,7 @@ constexpr int TL_FD = 4;        // forward ring depth
 constexpr int TL_BD = 4;        // backward ring depth
 
 constexpr int TL_R = 24;                       // a pixel displaced farther than this from the tile's anchor is SLOW
-constexpr int TL_ROWS = TL_TH + 2 * TL_R + 2;  // 66 source rows an inlier tap can touch: window [i0 + ady - R, ...)
+constexpr int TL_ROWS = TL_TH + 2 * TL_R + 2;  // <= 66 source rows an inlier tap can touch: window [i0 + ady - R, ...)
 constexpr int TL_ROWS_P = 96;                  // padded: 3 rows per lane in the scan
 constexpr int TL_ZPAD = 16;                    // zero cells in front of every stage (target of tap-less pixels)
 constexpr int TL_SK4 = 3;                      // row skew in pieces: cell (x, row r) sits at offset == x + 12 r (mod 32)
@@ -63,14 +63,14 @@ struct TileTab {
   int pad;
 };
 
-template <int NDIRS>
+template <int NDIRS, int PPT, int SLOTS>
 struct TileCtx {
   int n, t, j;
-  int irow[TL_PPT];
-  bool inimg[TL_PPT], act[TL_PPT];
-  TilePix px[TL_PPT][NDIRS];
-  unsigned info[TL_SLOTS];  // piece tid + s*256: dir << 31 | y << 16 | zero-fill << 15 | col
-  int pdst[TL_SLOTS];       // float offset of that piece inside a stage
+  int irow[PPT];
+  bool inimg[PPT], act[PPT];
+  TilePix px[PPT][NDIRS];
+  unsigned info[SLOTS];  // piece tid + s*256: dir << 31 | y << 16 | zero-fill << 15 | col
+  int pdst[SLOTS];       // float offset of that piece inside a stage
   int total;                // pieces per channel, both directions
   int stage_f;              // floats per stage (zero pad + both directions' slots)
   int ok;
@@ -149,9 +149,9 @@ __device__ __forceinline__ void tile_tab_scan(TileTab& tb, int slot_start4) {
 // overwrite later: the caller must __syncthreads() between this call and the first copy.
 // The slow pixels' taps are written to slowtap from the fast taps (enough for the forward).
 // Host-checked: the in-plane offsets of flow / gate / blend fit in 32 bits.
-template <int NDIRS, bool ALIGN, bool BORDER>
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS>
 __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, StageSlow& slow, Tap (*slowtap)[NDIRS],
-                                              int budget_floats, int stages_needed, TileCtx<NDIRS>& cx) {
+                                              int budget_floats, int stages_needed, TileCtx<NDIRS, PPT, SLOTS>& cx) {
   const Geo& G = P.geo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   cx.j = blockIdx.x * TL_TW + (warp & 3) * 8 + (lane & 7);  // a warp covers an 8x4 patch (fewer bank conflicts than 32x1)
@@ -162,14 +162,14 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     cx.n = blockIdx.z / G.T;
     cx.t = blockIdx.z - cx.n * G.T;
   }
-  const int i0 = blockIdx.y * TL_TH;
+  const int i0 = blockIdx.y * (8 * PPT);
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) {
+  for (int q = 0; q < PPT; ++q) {
     cx.irow[q] = i0 + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
     cx.inimg[q] = cx.j < G.W && cx.irow[q] < G.H;
   }
-  int x0[TL_PPT][NDIRS], y0[TL_PPT][NDIRS];
-  unsigned vld[TL_PPT][NDIRS];
+  int x0[PPT][NDIRS], y0[PPT][NDIRS];
+  unsigned vld[PPT][NDIRS];
   if (threadIdx.x < NDIRS * TL_ROWS_P) {
     TileTab& T = tb[threadIdx.x >= TL_ROWS_P ? 1 : 0];
     const int r = threadIdx.x >= TL_ROWS_P ? threadIdx.x - TL_ROWS_P : threadIdx.x;
@@ -180,9 +180,9 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
   if (threadIdx.x == 0) slow.n = 0;
   __syncthreads();
   const float bx = base_coord(cx.j, G.W, G.stepx);
-  float by[TL_PPT];
+  float by[PPT];
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) by[q] = base_coord(cx.irow[q], G.H, G.stepy);
+  for (int q = 0; q < PPT; ++q) by[q] = base_coord(cx.irow[q], G.H, G.stepy);
   const float fW = (float)G.W, fW1 = (float)(G.W - 1), fH = (float)G.H, fH1 = (float)(G.H - 1);
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     const float* fyp = at.flow + D.flow_sc;
     const int fsh = (int)D.flow_sh, gsh = (int)D.gate_sh, bsh = (int)D.blend_sh;
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) {
+    for (int q = 0; q < PPT; ++q) {
       TilePix& px = cx.px[q][d];
       px.tx = px.ty = px.ux = px.uy = px.bl = 0.f;
       px.clip = 0u;
@@ -247,7 +247,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     ady[d] = ((int)(k << 21)) >> 21;
   }
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) {
+  for (int q = 0; q < PPT; ++q) {
     bool far = false;
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d)
@@ -294,7 +294,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     alloc += tb[NDIRS - 1].alloc4;
   }
   cx.stage_f = TL_ZPAD + 4 * alloc;
-  if (cx.total > TL_SLOTS * TL_THREADS || stages_needed * cx.stage_f > budget_floats) cx.ok = 0;
+  if (cx.total > SLOTS * TL_THREADS || stages_needed * cx.stage_f > budget_floats) cx.ok = 0;
   if (!cx.ok) return;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
@@ -302,7 +302,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     const int yb = i0 + ady[d] - TL_R;
     const int doff = d == 0 ? 0 : 4 * tb[0].alloc4;  // the second direction's slot follows the first one's
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) {
+    for (int q = 0; q < PPT; ++q) {
       cx.px[q][d].o0 = cx.px[q][d].o1 = 0;
       if (vld[q][d]) {
         const int r = y0[q][d] - yb;
@@ -313,7 +313,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
   }
   // which pieces this thread copies: piece k = tid + s*256 of the two directions' piece lists back to back
 #pragma unroll
-  for (int s = 0; s < TL_SLOTS; ++s) {
+  for (int s = 0; s < SLOTS; ++s) {
     const int k = threadIdx.x + s * TL_THREADS;
     cx.info[s] = 0x8000u;
     cx.pdst[s] = 0;
@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_co
   int ooff[TL_PPT];
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
   {
-    TileCtx<NDIRS> cx;
-    tile_prologue<NDIRS, ALIGN, BORDER>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_FD, cx);
+    TileCtx<NDIRS, TL_PPT, TL_SLOTS> cx;
+    tile_prologue<NDIRS, ALIGN, BORDER, TL_PPT, TL_SLOTS>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_FD, cx);
     n = cx.n, t = cx.t, j = cx.j;
     if (!cx.ok) {  // wild flow: the tile's source footprint does not fit -> gather from global memory
 #pragma unroll
@@ -517,8 +517,8 @@ __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, i
   scatter_atomic_px(Q, g, d, n, t, c, false, k, gw, 0.f);
 }
 
-template <int NDIRS, bool ALIGN, bool BORDER>
-__global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS>
+__global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
                                                                  int smem_floats) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
@@ -530,27 +530,27 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   const Geo& G = P.geo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int n, t, j, total, stage_f;
-  int irow[TL_PPT];
-  bool act[TL_PPT];
-  float tx[TL_PPT][NDIRS], ty[TL_PPT][NDIRS], ux[TL_PPT][NDIRS], uy[TL_PPT][NDIRS], bl[TL_PPT][NDIRS];
-  unsigned a0[TL_PPT][NDIRS], a1[TL_PPT][NDIRS];  // byte offsets inside a stage of the nw and sw taps
-  unsigned info[TL_SLOTS];
-  unsigned pd[TL_SLOTS];  // byte offset inside a stage of piece tid + s*256
+  int irow[PPT];
+  bool act[PPT];
+  float tx[PPT][NDIRS], ty[PPT][NDIRS], ux[PPT][NDIRS], uy[PPT][NDIRS], bl[PPT][NDIRS];
+  unsigned a0[PPT][NDIRS], a1[PPT][NDIRS];  // byte offsets inside a stage of the nw and sw taps
+  unsigned info[SLOTS];
+  unsigned pd[SLOTS];  // byte offset inside a stage of piece tid + s*256
   unsigned clipbits = 0u;  // 2 bits per (q, d): the coordinate gradient is zero (border clipping)
   {
-    TileCtx<NDIRS> cx;
-    tile_prologue<NDIRS, ALIGN, BORDER>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
+    TileCtx<NDIRS, PPT, SLOTS> cx;
+    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
     n = cx.n, t = cx.t, j = cx.j;
     if (!cx.ok) {
 #pragma unroll
-      for (int q = 0; q < TL_PPT; ++q)
+      for (int q = 0; q < PPT; ++q)
         if (cx.inimg[q]) bwd_fused_generic_pixel<NDIRS>(P, Q, n, t, cx.irow[q], j);
       return;
     }
     total = cx.total;
     stage_f = cx.stage_f;
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) {
+    for (int q = 0; q < PPT; ++q) {
       irow[q] = cx.irow[q];
       act[q] = cx.act[q];
 #pragma unroll
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
       }
     }
 #pragma unroll
-    for (int s = 0; s < TL_SLOTS; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       info[s] = cx.info[s];
       pd[s] = 4u * (unsigned)cx.pdst[s];
     }
@@ -599,44 +599,44 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   if (threadIdx.x >= 32 && threadIdx.x < 32 + slow.n) {  // the slow path of the backward needs the full taps (multipliers, raw flow)
     const int sidx = threadIdx.x - 32, pix = slow.pix[sidx];
 #pragma unroll
-    for (int d = 0; d < NDIRS; ++d) compute_tap(G, P.dir[d], n, t, blockIdx.y * TL_TH + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d]);
+    for (int d = 0; d < NDIRS; ++d) compute_tap(G, P.dir[d], n, t, blockIdx.y * (8 * PPT) + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d]);
   }
   bool has_bl[NDIRS];
-  float blmax[TL_PPT];
+  float blmax[PPT];
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) blmax[q] = 0.f;
+  for (int q = 0; q < PPT; ++q) blmax[q] = 0.f;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
     has_bl[d] = P.dir[d].blend != nullptr;
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) blmax[q] = fmaxf(blmax[q], has_bl[d] ? fabsf(bl[q][d]) : 1.0f);
+    for (int q = 0; q < PPT; ++q) blmax[q] = fmaxf(blmax[q], has_bl[d] ? fabsf(bl[q][d]) : 1.0f);
   }
-  float gix[TL_PPT][NDIRS], giy[TL_PPT][NDIRS], gbl[TL_PPT][NDIRS];
+  float gix[PPT][NDIRS], giy[PPT][NDIRS], gbl[PPT][NDIRS];
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q)
+  for (int q = 0; q < PPT; ++q)
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) gix[q][d] = giy[q][d] = gbl[q][d] = 0.f;
   __syncthreads();  // the tables in dynamic shared memory are dead from here on; tab / slowtap / amax_s are visible
   const int Cn = nchan_s, g0 = g0_s;
   // per-thread copy / flush plan (row strides are those of group g0: all groups agree)
-  int poff[TL_SLOTS], goff[TL_SLOTS];  // element offset of piece tid + s*256 in its src plane / grad_src plane, or PIECE_*
-  unsigned tsel[TL_SLOTS];
+  int poff[SLOTS], goff[SLOTS];  // element offset of piece tid + s*256 in its src plane / grad_src plane, or PIECE_*
+  unsigned tsel[SLOTS];
 #pragma unroll
-  for (int s = 0; s < TL_SLOTS; ++s) {
+  for (int s = 0; s < SLOTS; ++s) {
     const int d = piece_dir(info[s]);
     tsel[s] = 8u * (unsigned)d;
     const bool none = threadIdx.x + s * TL_THREADS >= total, zero = piece_zero(info[s]);
     poff[s] = none ? PIECE_NONE : zero ? PIECE_ZERO : piece_y(info[s]) * P.grp[g0].src_sh[d] + piece_col(info[s]);
     goff[s] = (none || zero) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
   }
-  int gooff[TL_PPT];
+  int gooff[PPT];
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) gooff[q] = irow[q] * Q.go_sh[g0] + j;
+  for (int q = 0; q < PPT; ++q) gooff[q] = irow[q] * Q.go_sh[g0] + j;
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned stage_b = 4u * (unsigned)stage_f;
   const unsigned acc_s = smem_s + TL_BD * stage_b;  // two accumulators, stage layout
 #pragma unroll
-  for (int s = 0; s < TL_SLOTS; ++s)
+  for (int s = 0; s < SLOTS; ++s)
     if (goff[s] >= 0) {  // the pieces this thread flushes start from zero (the rest of the accumulators is never read)
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + pd[s]), "r"(0) : "memory");
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + stage_b + pd[s]), "r"(0) : "memory");
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
     const bool live = cf < Cn;
     const unsigned te = tab_s + (unsigned)sizeof(TileChanB) * (unsigned)(live ? cf : 0);
 #pragma unroll
-    for (int s = 0; s < TL_SLOTS; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const float* base = reinterpret_cast<const float*>(tl_lds64(te + tsel[s]));
       cp_async16_if(smem_s + pd[s] + soff, base + max(poff[s], 0), poff[s] >= 0 ? 16 : 0, live && poff[s] != PIECE_NONE);
     }
@@ -658,12 +658,12 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
     const bool live = cf < Cn;
     const float* gp = tab[live ? cf : 0].go;
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) go[q] = (live && act[q]) ? __ldcs(gp + gooff[q]) : 0.f;
+    for (int q = 0; q < PPT; ++q) go[q] = (live && act[q]) ? __ldcs(gp + gooff[q]) : 0.f;
   };
   auto vote_amax = [&](const float* go, int slot) {
     float m = 0.f;
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q)  // NaN must win the max: compare the bit patterns (non-negative floats order like uints)
+    for (int q = 0; q < PPT; ++q)  // NaN must win the max: compare the bit patterns (non-negative floats order like uints)
       m = __uint_as_float(max(__float_as_uint(m), __float_as_uint(fabsf(go[q]) * blmax[q])));
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
     if (lane == 0 && mb != 0u) atomicMax(&amax_s[slot], mb);
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   auto flush = [&](int cf, unsigned ab, float Sinv) {
     const unsigned te = tab_s + (unsigned)sizeof(TileChanB) * (unsigned)cf + 16u;  // &tab[cf].gs[0]
 #pragma unroll
-    for (int s = 0; s < TL_SLOTS; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       if (goff[s] < 0) continue;
       const unsigned a = ab + pd[s];
       int4 u;
@@ -689,13 +689,13 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
 #pragma unroll
     for (int p = 0; p < TL_BD - 1; ++p, so += stage_b) issue(p, so);
   }
-  float go[TL_PPT], gn[TL_PPT];
+  float go[PPT], gn[PPT];
   load_go(0, go);
   vote_amax(go, 0);
   // slow pixels, while the first copies are in flight: one warp per pixel, lanes over the channels
   for (int s = warp; s < slow.n; s += TL_THREADS / 32) {
     const int pix = slow.pix[s];
-    const int si = blockIdx.y * TL_TH + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
+    const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
     bwdflow_slow_warp<NDIRS>(P, Q, n, t, si, sj, slowtap[s]);
     for (int cf = lane; cf < Cn; cf += 32) {
       const TileChanB& tc = tab[cf];
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
     for (int d = 0; d < NDIRS; ++d) want[d] = tc.gs[d] != nullptr;
     const float Sf = (finite && ab != 0u) ? S : 0.f;  // 0: nothing goes to the accumulator
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) {
+    for (int q = 0; q < PPT; ++q) {
 #pragma unroll
       for (int d = 0; d < NDIRS; ++d) {
         const float a = tl_lds(sb + a0[q][d]), b = tl_lds4(sb + a0[q][d]);
@@ -757,13 +757,13 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
       }
     }
     if (!finite) {  // inf / NaN in this channel's grad_out (rare): float atomics straight to global memory
-      for (int q = 0; q < TL_PPT; ++q)
+      for (int q = 0; q < PPT; ++q)
         for (int d = 0; d < NDIRS; ++d)
           if (tc.gs[d] != nullptr && act[q]) bwd_nonfinite_px(P, Q, n, t, irow[q], j, tc.g, tc.c, d, has_bl[d] ? go[q] * bl[q][d] : go[q]);
     }
     vote_amax(gn, (cf + 1) % 3);
 #pragma unroll
-    for (int q = 0; q < TL_PPT; ++q) go[q] = gn[q];
+    for (int q = 0; q < PPT; ++q) go[q] = gn[q];
     Sinv_prev = Sinv;
     flush_prev = finite && ab != 0u;
     soff += stage_b;
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) bwd_tile_kernel(const __grid_co
   const float mxc = ALIGN ? __fmul_rn((float)(G.W - 1), 0.5f) : __fmul_rn((float)G.W, 0.5f);
   const float myc = ALIGN ? __fmul_rn((float)(G.H - 1), 0.5f) : __fmul_rn((float)G.H, 0.5f);
 #pragma unroll
-  for (int q = 0; q < TL_PPT; ++q) {
+  for (int q = 0; q < PPT; ++q) {
     if (!act[q]) continue;
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {

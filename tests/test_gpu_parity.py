@@ -297,7 +297,7 @@ def test_deterministic_mode_bit_exact_run_to_run(pkg):
 
 
 # ---------------------------------------------------------------- every kernel variant stays parity-checked
-VARIANTS = ["", "pairfwd,pairflow,nofuse", "pairfwd,csr,nofuse", "generic,nofuse", "nofuse"]
+VARIANTS = ["", "notile", "pairbwd", "pairfwd,pairflow,nofuse", "pairfwd,csr,nofuse", "generic,nofuse", "nofuse"]
 
 
 @pytest.mark.parametrize("det", [False, True])
@@ -361,6 +361,37 @@ def test_kernel_variants_deterministic_bit_exact(pkg, monkeypatch, variant):
     for r in runs[1:]:
         for a, b in zip(runs[0], r):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("env", [{}, {"FWB_TILE_BWD_PPT": "1"}, {"FWB_TILE_FWD_KB": "8", "FWB_TILE_BWD_KB": "12"}])
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("shape", [(2, 37, 52), (1, 16, 32), (1, 130, 260)])
+def test_tile_kernels_ragged_shapes_and_fallbacks(pkg, oracle, monkeypatch, shape, pad, env):
+    """The default (shared-memory tile) kernels on shapes that are not multiples of the 32x16 tile, with 5 % of the
+    pixels thrown out of the image (slow pixels / tap-less pixels), in the 32x8 backward variant, and with a shared
+    memory budget so small that every tile takes the in-kernel generic path."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    N, H, W = shape
+    f0 = [synth.rgb(0, N, H, W), synth.seg(1, N, H, W, 5)]
+    f1 = [synth.rgb(10, N, H, W), synth.seg(11, N, H, W, 5)]
+    ff, fb = synth.flow(3, N, H, W, 6.0, oob_frac=0.05), synth.flow(4, N, H, W, 6.0, oob_frac=0.05)
+    mf, mb = synth.mask(2, N, H, W), synth.mask(12, N, H, W)
+    gos = [synth.grad(5 + i, a.shape) for i, a in enumerate(f0)]
+    ref = oracle.forward(list(zip(f0, f1)), [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode=pad)
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode=pad)
+    t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+    tff, tfb, tmf, tmb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+    outs = pkg.warp_blend(t0, t1, tff, tfb, tmf, tmb, padding_mode=pad)
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    for g in range(len(f0)):
+        assert relerr(outs[g], ref[g][:, 0]) <= FWD_TOL
+        assert relerr(t0[g].grad, rg["grad_srcs"][g][0][:, 0]) <= BWD_TOL
+        assert relerr(t1[g].grad, rg["grad_srcs"][g][1][:, 0]) <= BWD_TOL
+    assert relerr(tff.grad, rg["grad_flows"][0][:, :, 0]) <= BWD_TOL
+    assert relerr(tfb.grad, rg["grad_flows"][1][:, :, 0]) <= BWD_TOL
+    assert relerr(tmf.grad, rg["grad_blends"][0]) <= BWD_TOL
+    assert relerr(tmb.grad, rg["grad_blends"][1]) <= BWD_TOL
 
 
 def test_fused_backward_propagates_non_finite_grad_out(pkg):
