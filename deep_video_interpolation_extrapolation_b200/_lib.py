@@ -14,6 +14,7 @@ FWB_PAD_ZEROS, FWB_PAD_BORDER = 0, 1
 FWB_FLAG_DETERMINISTIC = 1
 FWB_FLAG_ATOMIC_SRC = 2  # grad_src by global atomics (ATen-style), for A/B measurements only
 FWB_FLAG_FUSED_BWD = 4  # backward_flow also produces grad_src (fused kernels 2+3, non-deterministic fast path)
+FWB_FLAG_GRAD_SRC_ZEROED = 8  # with FUSED_BWD: the caller already zeroed grad_src (e.g. overlapped with the forward)
 
 _f32p = C.POINTER(C.c_float)
 i64 = C.c_int64

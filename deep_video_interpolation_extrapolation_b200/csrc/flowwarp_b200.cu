@@ -614,7 +614,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
       }
     if (ok && any_src) {
       // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out)
-      for (int gi = 0; gi < p->n_groups; ++gi)
+      for (int gi = 0; gi < p->n_groups && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED); ++gi)
         for (int d = 0; d < p->n_dirs; ++d) {
           float* gs = Q.grad_src[gi][d];
           if (!gs) continue;

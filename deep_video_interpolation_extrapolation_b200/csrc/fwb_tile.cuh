@@ -283,9 +283,10 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     }
   }
   __syncthreads();
+  cx.ok = slow.n <= TL_MAXSLOW;
+  if (!cx.ok) return;  // wild flow (too many pixels far from the anchor): the caller goes generic; skip the tables
   if (warp < NDIRS) tile_tab_scan(tb[warp], 0);
   __syncthreads();
-  cx.ok = slow.n <= TL_MAXSLOW;
   const int tot0 = tb[0].total4;
   cx.total = tot0;
   int alloc = tb[0].alloc4;

@@ -22,6 +22,15 @@ def batch_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def chunk_slices(n: int, chunk: int):
+    """Consecutive `slice`s of at most `chunk` samples covering [0, n) (the host pipeline's batch chunks)."""
+    if chunk < 1:
+        raise ValueError("chunk must be >= 1")
+    if n < 0:
+        raise ValueError("negative batch")
+    return [slice(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+
+
 def shard(tensors: Sequence, rank: int, world: int):
     """Slice every tensor of a clip batch along dim 0 with `batch_slice` (views, no copies)."""
     if not tensors:

@@ -56,6 +56,9 @@ extern "C" {
 #define FWB_FLAG_FUSED_BWD 4u     /* fwb_warp_blend_backward_flow also produces grad_src (kernels 2+3 fused: shared-memory
                                    * fixed-point tiles + vector reductions, non-deterministic); fwb_warp_blend_backward_src
                                    * then returns at once.  Ignored with FWB_FLAG_DETERMINISTIC / FWB_FLAG_ATOMIC_SRC. */
+#define FWB_FLAG_GRAD_SRC_ZEROED 8u /* with FWB_FLAG_FUSED_BWD: every grad_src plane is already zero on entry (the caller
+                                   * zeroed it earlier, e.g. on a side stream while the forward ran), so the library skips
+                                   * its own memsets.  The fused backward ACCUMULATES into grad_src. */
 
 /* argument errors (negative return values) */
 #define FWB_E_NULL -1      /* a required pointer is NULL */

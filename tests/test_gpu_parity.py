@@ -457,3 +457,30 @@ def test_full_size_properties_config2(pkg):
     torch.autograd.backward(pkg.warp_blend(y0, y1, ff, fb, mf, mb, deterministic=True), gos)
     for a, b in zip(x0 + x1, y0 + y1):
         assert relerr(a.grad, b.grad) <= BWD_TOL
+
+
+# ---------------------------------------------------------------- host-buffer pipeline (the e2e path of bench.py)
+@pytest.mark.parametrize("chunk", [1, 2, 5])
+def test_host_pipeline_matches_oracle_and_device_op(pkg, oracle, chunk):
+    """HostWarpBlend (pinned host in, pinned host out, batch-chunked on three streams) returns what the oracle
+    computes; ragged last chunk (N=5, chunk=2) and a chunk larger than the batch included."""
+    N, H, W = 5, 40, 64
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    ref = oracle.forward(list(zip(f0, f1)), [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    h = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    pipe = pkg.HostWarpBlend("cuda:0", chunk=chunk)
+    for _ in range(2):  # the second call reuses the pinned result buffers
+        res = pipe.run([h(a) for a in f0], [h(a) for a in f1], h(ff), h(fb), h(mf), h(mb), [h(g) for g in gos])
+    for g in range(len(f0)):
+        assert not res["outs"][g].is_cuda
+        assert relerr(res["outs"][g], ref[g][:, 0]) <= FWD_TOL
+        assert relerr(res["grad_frames0"][g], rg["grad_srcs"][g][0][:, 0]) <= BWD_TOL
+        assert relerr(res["grad_frames1"][g], rg["grad_srcs"][g][1][:, 0]) <= BWD_TOL
+    assert relerr(res["grad_for_flow"], rg["grad_flows"][0][:, :, 0]) <= BWD_TOL
+    assert relerr(res["grad_back_flow"], rg["grad_flows"][1][:, :, 0]) <= BWD_TOL
+    assert relerr(res["grad_for_mask"], rg["grad_blends"][0]) <= BWD_TOL
+    assert relerr(res["grad_back_mask"], rg["grad_blends"][1]) <= BWD_TOL
+    assert pipe.h2d_bytes == sum(a.size * 4 for a in f0 + f1 + [ff, fb, mf, mb] + gos)
+    with pytest.raises(RuntimeError):
+        pipe.run([cu(a) for a in f0], [h(a) for a in f1], h(ff), h(fb), h(mf), h(mb), [h(g) for g in gos])

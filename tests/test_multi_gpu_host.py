@@ -89,3 +89,13 @@ def test_two_rank_gloo_sharding_matches_unsharded(oracle):
     assert np.array_equal(got_g, rg)
     assert tmax == 1.5  # max over ranks of (0.5, 1.5)
     assert sharding.job_throughput(10.0, 4, 2.0, world) == 40.0
+
+
+def test_chunk_slices_cover_the_batch():
+    for n in range(0, 12):
+        for c in (1, 2, 3, 16):
+            sl = sharding.chunk_slices(n, c)
+            assert [i for s in sl for i in range(s.start, s.stop)] == list(range(n))
+            assert all(0 < s.stop - s.start <= c for s in sl)
+    with pytest.raises(ValueError):
+        sharding.chunk_slices(4, 0)
