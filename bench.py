@@ -214,7 +214,7 @@ def run_reference_arm(args, cfg, rank, world):
 class CabiStep:
     """The three C-ABI entry points on preallocated device buffers (what the autograd op calls)."""
 
-    def __init__(self, inp, deterministic, pad="border", atomic_src=False, prezero=False):
+    def __init__(self, inp, deterministic, pad="border", atomic_src=False, zero="fwd"):
         import torch
         from deep_video_interpolation_extrapolation_b200 import _lib as L
         from deep_video_interpolation_extrapolation_b200._problem import fill_grads, fill_problem
@@ -239,11 +239,14 @@ class CabiStep:
                               flags=(L.FWB_FLAG_DETERMINISTIC if deterministic else
                                      (L.FWB_FLAG_ATOMIC_SRC if atomic_src else L.FWB_FLAG_FUSED_BWD)), ptr=ptr, strides=st)
         self.fused = not deterministic and not atomic_src
-        # prezero: grad_src is zeroed on a side stream WHILE the forward runs (inside the step), and the fused backward is
-        # told so (FWB_FLAG_GRAD_SRC_ZEROED) instead of zeroing it itself between the two kernels
-        self.prezero = bool(prezero) and self.fused
-        if self.prezero:
+        # who zeroes grad_src before the fused backward accumulates into it:
+        #   "fwd"    the forward kernel's tiles (fwb_warp_blend_forward_zero), backward told FWB_FLAG_GRAD_SRC_ZEROED (default:
+        #            what the autograd op does); "memset": the backward entry point's own memsets; "side": torch fills on a
+        #            side stream while the forward runs (A/B only)
+        self.zero = zero if self.fused else "memset"
+        if self.zero in ("fwd", "side"):
             self.p.flags |= L.FWB_FLAG_GRAD_SRC_ZEROED
+        if self.zero == "side":
             self.side = torch.cuda.Stream(dev)
             self.main = torch.cuda.current_stream(dev)
         self.q = fill_grads(self.p, grad_outs=gos, grad_srcs=self.g_srcs, grad_flows=self.g_flows, grad_gates=[None, None],
@@ -254,7 +257,10 @@ class CabiStep:
         self.stream = torch.cuda.current_stream(dev).cuda_stream
 
     def forward(self):
-        self.L.check(self.lib.fwb_warp_blend_forward(ctypes.byref(self.p), self.stream), "forward")
+        if self.zero == "fwd":
+            self.L.check(self.lib.fwb_warp_blend_forward_zero(ctypes.byref(self.p), ctypes.byref(self.q), self.stream), "forward_zero")
+        else:
+            self.L.check(self.lib.fwb_warp_blend_forward(ctypes.byref(self.p), self.stream), "forward")
 
     def backward_flow(self):
         self.L.check(self.lib.fwb_warp_blend_backward_flow(ctypes.byref(self.p), ctypes.byref(self.q), self.ws.data_ptr(),
@@ -265,7 +271,7 @@ class CabiStep:
                                                           self.ws_bytes, self.stream), "backward_src")
 
     def step(self):
-        if self.prezero:
+        if self.zero == "side":
             import torch
             self.side.wait_stream(self.main)  # the previous step's backward has consumed grad_src
             with torch.cuda.stream(self.side):
@@ -314,7 +320,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     inp = make_inputs(cfg, dev, seed=rank)
     ar_buf = torch.zeros(cfg["allreduce"], device=dev) if cfg["allreduce"] else None
     chain = cfg["chain"]
-    step = CabiStep(inp, args.deterministic, atomic_src=args.atomic_src, prezero=args.prezero)
+    step = CabiStep(inp, args.deterministic, atomic_src=args.atomic_src, zero=args.zero)
 
     def one_step():
         for _ in range(chain):  # config 3: K chained invocations per training step (runners/ExtraTrainer.py:254-310)
@@ -389,7 +395,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
                        "flow_sigma_px": cfg["sigma"], "chained_steps": chain, "padding_mode": "border", "align_corners": False,
-                       "deterministic": bool(args.deterministic), "parallelism": f"batch-sharded x{world}, no collective in the op",
+                       "deterministic": bool(args.deterministic), "grad_src_zeroing": step.zero, "parallelism": f"batch-sharded x{world}, no collective in the op",
                        "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.config), "peak_source": peak_src,
@@ -416,7 +422,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
 
 
 # launches of OUR kernels per step (see csrc/flowwarp_b200.cu)
-# fused: fwd_tile_kernel 1 + bwd_tile_kernel 1 (grad_src is zeroed by 4 cudaMemsetAsync nodes, not counted);
+# fused: fwd_tile_kernel 1 (also zero-fills grad_src) + bwd_tile_kernel 1 (--zero memset: 4 cudaMemsetAsync nodes, not counted);
 # split (deterministic): forward 1 + (table init 1 + emit 1 + kernel 2) + kernel 3 x2
 LAUNCHES_PER_STEP = {"fused": 1 + 1, "split": 1 + 3 + 2}
 
@@ -431,7 +437,9 @@ def main():
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--atomic-src", action="store_true", help="A/B: grad_src via the global-atomic scatter kernel")
     ap.add_argument("--sigma", type=float, default=None, help="override flow sigma in pixels")
-    ap.add_argument("--prezero", action="store_true", help="zero grad_src on a side stream while the forward runs")
+    ap.add_argument("--zero", default="fwd", choices=["fwd", "memset", "side"],
+                    help="who zero-fills grad_src before the fused backward: the forward kernel (default), the backward's "
+                         "memsets, or a side stream (A/B)")
     ap.add_argument("--e2e-chunk", type=int, default=1, help="clips per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")

@@ -75,6 +75,7 @@ SYMBOLS = (
     "fwb_version",
     "fwb_strerror",
     "fwb_warp_blend_forward",
+    "fwb_warp_blend_forward_zero",
     "fwb_sample_indices",
     "fwb_workspace_bytes",
     "fwb_warp_blend_backward_flow",
@@ -106,6 +107,8 @@ def load() -> C.CDLL:
     lib.fwb_strerror.argtypes = [C.c_int32]
     lib.fwb_warp_blend_forward.restype = C.c_int32
     lib.fwb_warp_blend_forward.argtypes = [pp, vp]
+    lib.fwb_warp_blend_forward_zero.restype = C.c_int32
+    lib.fwb_warp_blend_forward_zero.argtypes = [pp, gp, vp]
     lib.fwb_sample_indices.restype = C.c_int32
     lib.fwb_sample_indices.argtypes = [pp, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.fwb_workspace_bytes.restype = C.c_size_t

@@ -282,7 +282,7 @@ static dim3 stage_grid(const fwb_problem* p) {
 //   backward, determ.  generic kernel 2 + owner-gather kernel 3       ("pairflow": channel-pair kernel 2, "csr": list kernel 3)
 // FWB_KERNELS=<comma separated words> switches variants for A/B measurements and for the tests that keep every
 // variant parity-checked; read on every call (getenv is cheap next to a launch).
-enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_PAIRBWD = 64u };
+enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_PAIRBWD = 64u, KN_NOZFUSE = 128u };
 static unsigned knobs() {
   const char* v = getenv("FWB_KERNELS");
   if (!v || !*v) return 0u;
@@ -294,6 +294,7 @@ static unsigned knobs() {
   if (strstr(v, "generic")) k |= KN_GENERIC;
   if (strstr(v, "notile")) k |= KN_NOTILE;
   if (strstr(v, "pairbwd")) k |= KN_PAIRBWD;
+  if (strstr(v, "nozfuse")) k |= KN_NOZFUSE;
   return k;
 }
 static int env_int(const char* name, int dflt) {
@@ -370,6 +371,27 @@ static int set_smem(K kernel, int bytes) {
 }  // namespace fwb
 
 using namespace fwb;
+
+// zero every grad_src plane present (memset when contiguous, a row kernel otherwise)
+static int32_t zero_grad_src(const fwb_problem* p, const GradP& Q, cudaStream_t s) {
+  for (int gi = 0; gi < p->n_groups; ++gi)
+    for (int d = 0; d < p->n_dirs; ++d) {
+      float* gs = Q.grad_src[gi][d];
+      if (!gs) continue;
+      const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
+      const long long C = p->grp[gi].C, HW = (long long)p->H * p->W;
+      if (Q.gs_sh[gi][d] == p->W && Q.gs_sc[gi][d] == HW && (Tn == 1 || Q.gs_st[gi][d] == C * HW) &&
+          (p->N == 1 || Q.gs_sn[gi][d] == Tn * C * HW)) {  // contiguous: one memset at full write bandwidth
+        const int32_t rc = (int32_t)cudaMemsetAsync(gs, 0, (size_t)(p->N * Tn * C * HW) * sizeof(float), s);
+        if (rc) return rc;
+        continue;
+      }
+      const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
+      zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d], p->N, Tn,
+                                          p->grp[gi].C, p->H, p->W);
+    }
+  return (int32_t)cudaGetLastError();
+}
 
 static int32_t run_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace, size_t workspace_bytes,
                                 void* stream) {
@@ -509,25 +531,55 @@ const char* fwb_strerror(int32_t code) {
   }
 }
 
-int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
+}  // extern "C"
+
+// the forward, optionally with the zero-fill of zq->grad_src as a side job (zq == NULL: plain forward)
+static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stream) {
   int rc = validate(p);
   if (rc) return rc;
   for (int g = 0; g < p->n_groups; ++g) {
     if (!p->grp[g].out) return FWB_E_NULL;
     if ((uintptr_t)p->grp[g].out & 3u) return FWB_E_ALIGN;
   }
-  if (p->N == 0) return 0;
   Params P;
   to_params(p, P);
+  GradP Q;
+  if (zq && (rc = to_grads(p, zq, Q))) return rc;
+  if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!(knobs() & (KN_PAIRFWD | KN_NOTILE)) && stage_ok(p) && tile_fwd_ok(p)) {
+  const bool tile = !(knobs() & (KN_PAIRFWD | KN_NOTILE)) && stage_ok(p) && tile_fwd_ok(p);
+  ZeroP Z;
+  memset(&Z, 0, sizeof(Z));
+  if (zq) {
+    // in-kernel zero-fill needs 16-byte aligned rows and one row stride per direction; anything else: memsets first
+    bool fuse = tile && !(knobs() & KN_NOZFUSE), any = false;
+    int sh[2] = {0, 0};
+    for (int g = 0; g < p->n_groups; ++g)
+      for (int d = 0; d < p->n_dirs; ++d) {
+        float* gs = Q.grad_src[g][d];
+        if (!gs) continue;
+        any = true;
+        if (((uintptr_t)gs & 15u) || (Q.gs_sn[g][d] & 3) || (Q.gs_st[g][d] & 3) || (Q.gs_sc[g][d] & 3) || (Q.gs_sh[g][d] & 3)) fuse = false;
+        if (sh[d] == 0) sh[d] = Q.gs_sh[g][d];
+        if (sh[d] != Q.gs_sh[g][d] || (long long)(p->H + 1) * Q.gs_sh[g][d] >= 2147483647LL) fuse = false;
+        Z.gs[g][d] = gs;
+        Z.sn[g][d] = Q.gs_sn[g][d];
+        Z.st[g][d] = Q.gs_st[g][d];
+        Z.sc[g][d] = Q.gs_sc[g][d];
+      }
+    Z.sh[0] = sh[0];
+    Z.sh[1] = sh[1];
+    Z.on = (fuse && any) ? 1 : 0;
+    if (any && !Z.on && (rc = zero_grad_src(p, Q, s))) return rc;
+  }
+  if (tile) {
     const int sb = env_int("FWB_TILE_FWD_KB", 52) * 1024;
     const int Ctot = total_channels(p);
     const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + TL_TH - 1) / TL_TH, p->N * p->T);
 #define FWB_LAUNCH_TFWD(D, A, B)                                                     \
   do {                                                                               \
     if ((rc = set_smem(fwd_tile_kernel<D, A, B>, sb))) return rc;                    \
-    fwd_tile_kernel<D, A, B><<<grid, TL_THREADS, sb, s>>>(P, sb / 4, Ctot);          \
+    fwd_tile_kernel<D, A, B><<<grid, TL_THREADS, sb, s>>>(P, sb / 4, Ctot, Z);       \
   } while (0)
     const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
     switch (key) {
@@ -572,6 +624,15 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) {
   return (int32_t)cudaGetLastError();
 }
 
+extern "C" {
+
+int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) { return run_forward(p, nullptr, stream); }
+
+int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, void* stream) {
+  if (!g) return FWB_E_NULL;
+  return run_forward(p, g, stream);
+}
+
 int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0, uint8_t* valid,
                            float* ix, float* iy, void* stream) {
   int rc = validate(p);
@@ -613,22 +674,9 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
           ok = false;  // red.global.add.v4.f32 needs 16-byte aligned rows
       }
     if (ok && any_src) {
-      // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out)
-      for (int gi = 0; gi < p->n_groups && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED); ++gi)
-        for (int d = 0; d < p->n_dirs; ++d) {
-          float* gs = Q.grad_src[gi][d];
-          if (!gs) continue;
-          const int Tn = Q.gs_st[gi][d] == 0 ? 1 : p->T;
-          const long long C = p->grp[gi].C, HW = (long long)p->H * p->W;
-          if (Q.gs_sh[gi][d] == p->W && Q.gs_sc[gi][d] == HW && (Tn == 1 || Q.gs_st[gi][d] == C * HW) &&
-              (p->N == 1 || Q.gs_sn[gi][d] == Tn * C * HW)) {  // contiguous: one memset at copy-engine-free full write bandwidth
-            if ((rc = (int32_t)cudaMemsetAsync(gs, 0, (size_t)(p->N * Tn * C * HW) * sizeof(float), s))) return rc;
-            continue;
-          }
-          const dim3 zg((unsigned)(p->N * Tn * p->grp[gi].C), (unsigned)(p->H < 64 ? p->H : 64));
-          zero_rows_kernel<<<zg, 256, 0, s>>>(gs, Q.gs_sn[gi][d], Q.gs_st[gi][d], Q.gs_sc[gi][d], Q.gs_sh[gi][d], p->N, Tn,
-                                              p->grp[gi].C, p->H, p->W);
-        }
+      // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out) unless the
+      // caller did (FWB_FLAG_GRAD_SRC_ZEROED, e.g. fwb_warp_blend_forward_zero)
+      if (!(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
       if (!(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g)) {
         const int ppt = env_int("FWB_TILE_BWD_PPT", 2);  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
         const int sb = env_int("FWB_TILE_BWD_KB", ppt == 1 ? 48 : 80) * 1024;

@@ -373,11 +373,42 @@ constexpr int PIECE_ZERO = -1, PIECE_NONE = -2;
 struct TileChanF {
   const float* src[2];
   float* out;
-  long long pad;
+  float* z[2];  // grad_src plane of this channel per direction to zero-fill (NULL: none), see ZeroP
 };
 
+// Optional side job of the forward: zero-fill the grad_src planes the fused backward will accumulate into.  Every tile
+// clears the 32x16 block of its own output coordinates in every plane (one 16-byte store per thread and channel, riding
+// on the forward's spare store bandwidth), so the backward needs no memset pass between the two kernels.
+struct ZeroP {
+  float* gs[FWB_MAX_GROUPS][2];
+  long long sn[FWB_MAX_GROUPS][2], st[FWB_MAX_GROUPS][2];
+  int sc[FWB_MAX_GROUPS][2];
+  int sh[2];  // row stride per direction (all groups agree, host-checked)
+  int on;
+};
+
+// element offset inside a grad_src plane of the 4 floats thread `tid` clears for direction *zd, or -1
+template <int NDIRS>
+__device__ __forceinline__ int zero_plan(const Geo& G, const ZeroP& Z, int* zd) {
+  const int tid = threadIdx.x;
+  *zd = tid >> 7;
+  if (!Z.on || *zd >= NDIRS) return -1;
+  const int i = blockIdx.y * TL_TH + ((tid >> 3) & 15), j = blockIdx.x * TL_TW + (tid & 7) * 4;
+  return (i < G.H && j < G.W) ? i * Z.sh[*zd] + j : -1;
+}
+__device__ __forceinline__ float* zero_plane(const ZeroP& Z, const Geo& G, int g, int d, int n, int t, int c) {
+  float* p = Z.gs[g][d];
+  if (!p || (t != 0 && Z.st[g][d] == 0)) return nullptr;  // a source shared by all T frames is cleared by the t == 0 tiles
+  return p + n * Z.sn[g][d] + t * Z.st[g][d] + (long long)c * Z.sc[g][d];
+}
+__device__ __forceinline__ void st_zero4_if(float* p, bool on) {
+  asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %1, 0;\n @pp st.global.v4.f32 [%0], {%2,%2,%2,%2};\n}\n" ::"l"(p), "r"((int)on), "f"(0.f)
+               : "memory");
+}
+
 template <int NDIRS, bool ALIGN, bool BORDER>
-__global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_constant__ Params P, int smem_floats, int Ctot) {
+__global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_constant__ Params P, int smem_floats, int Ctot,
+                                                                 const __grid_constant__ ZeroP Z) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
   __shared__ StageSlow slow;
@@ -400,6 +431,14 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_co
 #pragma unroll
       for (int q = 0; q < TL_PPT; ++q)
         if (cx.inimg[q]) fwd_generic_pixel<NDIRS>(P, n, t, cx.irow[q], j);
+      int zd;
+      const int zo = zero_plan<NDIRS>(P.geo, Z, &zd);
+      if (zo >= 0)
+        for (int g = 0; g < P.geo.n_groups; ++g)
+          for (int c = 0; c < P.grp[g].C; ++c) {
+            float* zp = zero_plane(Z, P.geo, g, zd, n, t, c);
+            if (zp) st_zero4_if(zp + zo, true);
+          }
       return;
     }
     stage_f = cx.stage_f;
@@ -438,12 +477,16 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_co
 #pragma unroll
     for (int d = 0; d < 2; ++d) e.src[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d];
     e.out = R.out + n * R.out_sn + t * R.out_st + (long long)c * R.out_sc;
-    e.pad = 0;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) e.z[d] = (Z.on && d < NDIRS) ? zero_plane(Z, P.geo, g, d, n, t, c) : nullptr;
     tab[threadIdx.x] = e;
   }
   bool has_bl[NDIRS];
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) has_bl[d] = P.dir[d].blend != nullptr;
+  int zdir;
+  const int zoff = zero_plan<NDIRS>(P.geo, Z, &zdir);
+  const unsigned zsel = 8u + 8u * (unsigned)zdir;  // &tab[cf].z[zdir] relative to &tab[cf].out
   __syncthreads();  // the tables in dynamic shared memory are dead from here on; tab / slowtap are visible
   if (threadIdx.x < TL_FD * TL_ZPAD) smem[(threadIdx.x / TL_ZPAD) * stage_f + (threadIdx.x % TL_ZPAD)] = 0.f;
   const unsigned stage_b = 4u * (unsigned)stage_f;
@@ -463,6 +506,15 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_co
     unsigned so = 0;
 #pragma unroll
     for (int p = 0; p < TL_FD - 1; ++p, so += stage_b) issue(p, so);
+  }
+  // zero-fill of the grad_src blocks (side job, Z.on): fire-and-forget stores while the first copies are in flight
+  if (zoff >= 0) {
+    unsigned tz = tab_s + 16u + zsel;
+#pragma unroll 4
+    for (int cf = 0; cf < Ctot; ++cf, tz += (unsigned)sizeof(TileChanF)) {
+      float* const zp = reinterpret_cast<float*>(tl_lds64(tz));
+      st_zero4_if(zp + zoff, zp != nullptr);
+    }
   }
   // slow pixels, while the first copies are in flight: one (pixel, channel) item per thread
   for (int it = threadIdx.x; it < slow.n * Ctot; it += TL_THREADS) {

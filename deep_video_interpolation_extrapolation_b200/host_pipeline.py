@@ -47,7 +47,8 @@ class _Slot:
         self.used = False
         self.lib = L.load()
         pad = L.FWB_PAD_BORDER if kw["padding_mode"] == "border" else L.FWB_PAD_ZEROS
-        flags = L.FWB_FLAG_DETERMINISTIC if kw["deterministic"] else L.FWB_FLAG_FUSED_BWD
+        self.fused = not kw["deterministic"]  # fused backward: the forward zero-fills grad_src (no memset pass)
+        flags = L.FWB_FLAG_DETERMINISTIC if kw["deterministic"] else (L.FWB_FLAG_FUSED_BWD | L.FWB_FLAG_GRAD_SRC_ZEROED)
         ptr, st = (lambda t: t.data_ptr()), (lambda t: t.stride())
         self.structs = {}
         for m in sorted({n} | ({kw["tail"]} if kw.get("tail") else set())):  # full chunk and the ragged last chunk
@@ -70,7 +71,10 @@ class _Slot:
     def launch(self, m, stream_ptr):
         p, q = self.structs[m]
         lib = self.lib
-        L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), stream_ptr), "fwb_warp_blend_forward")
+        if self.fused:
+            L.check(lib.fwb_warp_blend_forward_zero(ctypes.byref(p), ctypes.byref(q), stream_ptr), "fwb_warp_blend_forward_zero")
+        else:
+            L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), stream_ptr), "fwb_warp_blend_forward")
         L.check(lib.fwb_warp_blend_backward_flow(ctypes.byref(p), ctypes.byref(q), self.ws.data_ptr(), self.ws_bytes, stream_ptr),
                 "fwb_warp_blend_backward_flow")
         L.check(lib.fwb_warp_blend_backward_src(ctypes.byref(p), ctypes.byref(q), self.ws.data_ptr(), self.ws_bytes, stream_ptr),

@@ -26,6 +26,11 @@ Tensor = torch.Tensor
 # the (deterministic) owner-gather kernel.  Not a fallback: both are CUDA kernels of this library.
 ATOMIC_SRC = False
 
+# True: when a source requires grad (and the fused backward will be used) the forward call allocates grad_src and lets
+# the forward kernel zero-fill it (fwb_warp_blend_forward_zero), so the backward runs without a memset pass.  Costs the
+# grad_src buffers being alive between forward and backward; False restores "allocate and zero in backward".
+PREZERO_GRAD_SRC = True
+
 
 def _flags(cfg) -> int:
     if cfg.deterministic:
@@ -74,6 +79,13 @@ def _stream_ptr(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _alloc_grad_src(s: Tensor, cfg) -> Tensor:
+    """grad buffer of source `s` ([N,T,C,H,W]; T-stride 0 = one frame shared by all T -> one summed plane set)."""
+    shared = s.stride(1) == 0 and cfg.T > 1
+    buf = torch.empty((cfg.N, 1 if shared else cfg.T, s.shape[2], cfg.H, cfg.W), dtype=torch.float32, device=s.device)
+    return buf.expand(cfg.N, cfg.T, s.shape[2], cfg.H, cfg.W) if shared else buf
+
+
 class _WarpBlendFn(torch.autograd.Function):
     """tensors = flows[D] + gates[D] + blends[D] + srcs[G*D] (g-major); all already canonical 5-D/4-D."""
 
@@ -93,7 +105,18 @@ class _WarpBlendFn(torch.autograd.Function):
                              align_corners=cfg.align_corners,
                              flags=_flags(cfg),
                              ptr=_ptr, strides=_strides)
-            L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), _stream_ptr(dev)), "fwb_warp_blend_forward")
+            need_src = ctx.needs_input_grad[1 + 3 * D:]
+            pre = None
+            if PREZERO_GRAD_SRC and _flags(cfg) == L.FWB_FLAG_FUSED_BWD and any(need_src):
+                pre = [[_alloc_grad_src(srcs[g][d], cfg) if need_src[g * D + d] else None for d in range(D)]
+                       for g in range(G)]
+                q = fill_grads(p, grad_outs=[None] * G, grad_srcs=pre, grad_flows=[None] * D, grad_gates=[None] * D,
+                               grad_blends=[None] * D, ptr=_ptr, strides=_strides)
+                L.check(lib.fwb_warp_blend_forward_zero(ctypes.byref(p), ctypes.byref(q), _stream_ptr(dev)),
+                        "fwb_warp_blend_forward_zero")
+            else:
+                L.check(lib.fwb_warp_blend_forward(ctypes.byref(p), _stream_ptr(dev)), "fwb_warp_blend_forward")
+        ctx.pre_gsrcs = pre
         ctx.cfg = cfg
         ctx.save_for_backward(*[t for t in tensors if t is not None])
         ctx.present = [t is not None for t in tensors]
@@ -120,25 +143,24 @@ class _WarpBlendFn(torch.autograd.Function):
                    for d in range(D)]
         g_blends = [torch.empty((N, T, H, W), **f32) if (need[2 * D + d] and blends[d] is not None) else None
                     for d in range(D)]
+        pre, ctx.pre_gsrcs = ctx.pre_gsrcs, None  # zero-filled by the forward; good for ONE backward
         g_srcs: List[List[Optional[Tensor]]] = []
         for g in range(G):
             row = []
             for d in range(D):
-                s = srcs[g][d]
                 if need[3 * D + g * D + d] and gos[g] is not None:
-                    shared = s.stride(1) == 0 and T > 1
-                    buf = torch.empty((N, 1 if shared else T, s.shape[2], H, W), **f32)
-                    row.append(buf.expand(N, T, s.shape[2], H, W) if shared else buf)
+                    row.append(pre[g][d] if pre is not None else _alloc_grad_src(srcs[g][d], cfg))
                 else:
                     row.append(None)
             g_srcs.append(row)
+        flags = _flags(cfg) | (L.FWB_FLAG_GRAD_SRC_ZEROED if pre is not None else 0)
 
         lib = L.load()
         with torch.cuda.device(dev):
             p = fill_problem(N=N, T=T, H=H, W=W, flows=flows, gates=gates, blends=blends, signs=cfg.signs,
                              srcs=srcs, outs=None, padding_mode=cfg.padding_mode,
                              align_corners=cfg.align_corners,
-                             flags=_flags(cfg),
+                             flags=flags,
                              ptr=_ptr, strides=_strides)
             q = fill_grads(p, grad_outs=gos, grad_srcs=g_srcs, grad_flows=g_flows, grad_gates=g_gates,
                            grad_blends=g_blends, ptr=_ptr, strides=_strides)

@@ -131,6 +131,13 @@ const char* fwb_strerror(int32_t code);
  * Replaces utils/net_utils.py:93-121 (+124-129) and nets/OpticalUnet.py:123-146. */
 int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream);
 
+/* The same forward, which additionally sets every grad_src plane named in `g` to zero (only g->grad_src and its
+ * strides are read).  torch zero-fills the gradient of grid_sample's input before its atomicAdd scatter
+ * (ATen grid_sampler_2d_backward, reached from utils/net_utils.py:113 by autograd); here the forward's tiles do it
+ * with spare store bandwidth, so the fused backward can be called with FWB_FLAG_GRAD_SRC_ZEROED and needs no memset
+ * pass.  Planes the kernel cannot clear in place (unaligned / odd strides) are cleared by memsets on `stream`. */
+int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, void* stream);
+
 /* Debug / parity: integer sample indices and validity bits of direction `d`.
  * x0,y0: int32 [N,T,H,W] contiguous; valid: uint8 [N,T,H,W], bit0 nw, bit1 ne, bit2 sw, bit3 se.
  * Same device function as the forward kernel. */

@@ -484,3 +484,73 @@ def test_host_pipeline_matches_oracle_and_device_op(pkg, oracle, chunk):
     assert pipe.h2d_bytes == sum(a.size * 4 for a in f0 + f1 + [ff, fb, mf, mb] + gos)
     with pytest.raises(RuntimeError):
         pipe.run([cu(a) for a in f0], [h(a) for a in f1], h(ff), h(fb), h(mf), h(mb), [h(g) for g in gos])
+
+
+# ---------------------------------------------------------------- grad_src zero-fill fused into the forward
+@pytest.mark.parametrize("shape,sigma,T", [((2, 48, 64), 8.0, 1), ((1, 37, 52), 8.0, 1), ((1, 33, 50), 8.0, 1),
+                                           ((1, 64, 96), 300.0, 1), ((2, 40, 64), 6.0, 3)])
+def test_forward_zero_clears_every_grad_src_plane(pkg, oracle, shape, sigma, T):
+    """fwb_warp_blend_forward_zero: same outputs as the plain forward, and every grad_src plane is exactly zero
+    afterwards whatever it held (NaN here) - tile path, ragged tiles, W % 4 != 0 (memset path), wild flows (per-tile
+    generic path inside the tile kernel), T frames sharing one source (T-stride 0)."""
+    import ctypes
+    from deep_video_interpolation_extrapolation_b200 import _lib as L
+    from deep_video_interpolation_extrapolation_b200._problem import fill_grads, fill_problem
+    lib = L.load()
+    N, H, W = shape
+    Cs = (3, 5)
+    five = lambda a: a.unsqueeze(1)  # noqa: E731
+    if T == 1:
+        srcs = [[five(cu(synth.rgb(10 * g + d, N, H, W, c))) for d in range(2)] for g, c in enumerate(Cs)]
+        flows = [cu(synth.flow(3 + d, N, H, W, sigma)).unsqueeze(2) for d in range(2)]
+        blends = [cu(synth.mask(2 + d, N, H, W)) for d in range(2)]
+        gsrc = [[torch.full((N, 1, c, H, W), float("nan"), device="cuda") for _ in range(2)] for c in Cs]
+    else:  # one source frame feeds all T flows: source and grad_src have T-stride 0
+        srcs = [[five(cu(synth.rgb(10 * g + d, N, H, W, c))).expand(N, T, c, H, W) for d in range(2)] for g, c in enumerate(Cs)]
+        flows = [cu(synth.flow(3 + d, N, H, W, sigma, T=T)) for d in range(2)]
+        blends = [cu(synth.mask(2 + d, N, H, W, T=T)) for d in range(2)]
+        gsrc = [[torch.full((N, 1, c, H, W), float("nan"), device="cuda").expand(N, T, c, H, W) for _ in range(2)] for c in Cs]
+    outs_a = [torch.empty(N, T, c, H, W, device="cuda") for c in Cs]
+    outs_b = [torch.empty(N, T, c, H, W, device="cuda") for c in Cs]
+    ptr, st = (lambda t: t.data_ptr()), (lambda t: t.stride())
+    mk = lambda outs: fill_problem(N=N, T=T, H=H, W=W, flows=flows, gates=[None, None], blends=blends, signs=[-1.0, 1.0],  # noqa: E731
+                                   srcs=srcs, outs=outs, padding_mode=L.FWB_PAD_BORDER, align_corners=False,
+                                   flags=L.FWB_FLAG_FUSED_BWD, ptr=ptr, strides=st)
+    pa, pb = mk(outs_a), mk(outs_b)
+    q = fill_grads(pb, grad_outs=[None, None], grad_srcs=gsrc, grad_flows=[None, None], grad_gates=[None, None],
+                   grad_blends=[None, None], ptr=ptr, strides=st)
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.fwb_warp_blend_forward(ctypes.byref(pa), s), "forward")
+    L.check(lib.fwb_warp_blend_forward_zero(ctypes.byref(pb), ctypes.byref(q), s), "forward_zero")
+    torch.cuda.synchronize()
+    for a, b in zip(outs_a, outs_b):
+        assert torch.equal(a, b)
+    for row in gsrc:
+        for g in row:
+            assert torch.count_nonzero(g[:, :1] if T > 1 else g).item() == 0 and not torch.isnan(g).any()
+
+
+def test_backward_twice_and_prezero_switch(pkg, monkeypatch):
+    """The zero-filled grad_src buffers of the forward serve ONE backward; a second backward (retain_graph) and the
+    PREZERO_GRAD_SRC=False path must give the same gradients."""
+    from deep_video_interpolation_extrapolation_b200 import ops
+    N, H, W = 2, 48, 64
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    tg = [cu(g) for g in gos]
+
+    def run(twice):
+        t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+        outs = pkg.warp_blend(t0, t1, cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True), deterministic=False)
+        if twice:
+            torch.autograd.backward(outs, tg, retain_graph=True)
+            for t in t0 + t1:
+                t.grad = None
+        torch.autograd.backward(outs, tg)
+        return [t.grad.clone() for t in t0 + t1]
+
+    a = run(False)
+    b = run(True)
+    monkeypatch.setattr(ops, "PREZERO_GRAD_SRC", False)
+    c = run(False)
+    for x, y, z in zip(a, b, c):
+        assert relerr(y, x) <= BWD_TOL and relerr(z, x) <= BWD_TOL
