@@ -67,6 +67,20 @@ class fwb_grads(C.Structure):
     ]
 
 
+class fwb_blend(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("Cn", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("input", C.c_void_p), ("in_sn", i64), ("in_st", i64), ("in_sc", i64), ("in_sh", i64),
+        ("mask", C.c_void_p), ("m_sn", i64), ("m_st", i64), ("m_sh", i64),
+        ("noise", C.c_void_p), ("nz_sn", i64), ("nz_sc", i64), ("nz_sh", i64),
+        ("out", C.c_void_p), ("out_sn", i64), ("out_st", i64), ("out_sc", i64), ("out_sh", i64),
+        ("grad_out", C.c_void_p), ("go_sn", i64), ("go_st", i64), ("go_sc", i64), ("go_sh", i64),
+        ("grad_input", C.c_void_p), ("gi_sn", i64), ("gi_st", i64), ("gi_sc", i64), ("gi_sh", i64),
+        ("grad_mask", C.c_void_p), ("gm_sn", i64), ("gm_st", i64), ("gm_sh", i64),
+        ("grad_noise", C.c_void_p), ("gn_sn", i64), ("gn_sc", i64), ("gn_sh", i64),
+    ]
+
+
 LIB_NAME = "libflowwarp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
@@ -76,6 +90,8 @@ SYMBOLS = (
     "fwb_strerror",
     "fwb_warp_blend_forward",
     "fwb_warp_blend_forward_zero",
+    "fwb_mask_blend_forward",
+    "fwb_mask_blend_backward",
     "fwb_sample_indices",
     "fwb_workspace_bytes",
     "fwb_warp_blend_backward_flow",
@@ -109,6 +125,11 @@ def load() -> C.CDLL:
     lib.fwb_warp_blend_forward.argtypes = [pp, vp]
     lib.fwb_warp_blend_forward_zero.restype = C.c_int32
     lib.fwb_warp_blend_forward_zero.argtypes = [pp, gp, vp]
+    bp = C.POINTER(fwb_blend)
+    lib.fwb_mask_blend_forward.restype = C.c_int32
+    lib.fwb_mask_blend_forward.argtypes = [bp, vp]
+    lib.fwb_mask_blend_backward.restype = C.c_int32
+    lib.fwb_mask_blend_backward.argtypes = [bp, vp]
     lib.fwb_sample_indices.restype = C.c_int32
     lib.fwb_sample_indices.argtypes = [pp, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.fwb_workspace_bytes.restype = C.c_size_t

@@ -19,6 +19,7 @@
 #include "fwb_pair.cuh"
 #include "fwb_csr.cuh"
 #include "fwb_tile.cuh"
+#include "fwb_blend.cuh"
 
 namespace fwb {
 
@@ -631,6 +632,34 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) { return run_
 int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, void* stream) {
   if (!g) return FWB_E_NULL;
   return run_forward(p, g, stream);
+}
+
+int32_t fwb_mask_blend_forward(const fwb_blend* b, void* stream) {
+  int rc = blend_validate(b, false);
+  if (rc) return rc;
+  if (b->N == 0) return 0;
+  BlendP B;
+  blend_params(b, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (blend_vec_ok(b, false))
+    mask_blend_fwd_kernel<4><<<dim3((b->W / 4 + 127) / 128, b->H, b->N * b->T), 128, 0, s>>>(B);
+  else
+    mask_blend_fwd_kernel<1><<<dim3((b->W + 127) / 128, b->H, b->N * b->T), 128, 0, s>>>(B);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_mask_blend_backward(const fwb_blend* b, void* stream) {
+  int rc = blend_validate(b, true);
+  if (rc) return rc;
+  if (b->N == 0 || (!b->grad_input && !b->grad_mask && !b->grad_noise)) return 0;
+  BlendP B;
+  blend_params(b, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (blend_vec_ok(b, true))
+    mask_blend_bwd_kernel<4, 4><<<dim3((b->W / 4 + 127) / 128, b->H, b->N), 128, 0, s>>>(B);
+  else
+    mask_blend_bwd_kernel<1, 4><<<dim3((b->W + 127) / 128, b->H, b->N), 128, 0, s>>>(B);
+  return (int32_t)cudaGetLastError();
 }
 
 int32_t fwb_sample_indices(const fwb_problem* p, int32_t d, int32_t* x0, int32_t* y0, uint8_t* valid,

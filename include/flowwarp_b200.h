@@ -120,6 +120,32 @@ typedef struct fwb_grads {
   int64_t gb_sn[2], gb_st[2], gb_sh[2];
 } fwb_grads;
 
+/* The mask blend that follows the warp in `refine` (utils/net_utils.py:141-143):
+ *     out[n,t,c] = input[n,t,c] * mask[n,t] + noise[n,c] * (1 - mask[n,t])
+ * with the `cat([noise_bg, zeros(20)])` of `:134-136` folded in: only the first Cn <= C channels have a noise plane,
+ * the others blend against zero.  All strides in elements, W-stride 1.  Forward reads input/mask/noise and writes
+ * out; backward reads grad_out (+ input, mask, noise) and writes whichever of grad_input / grad_mask / grad_noise
+ * is non-NULL.  Both are single streaming passes, deterministic (no atomics). */
+typedef struct fwb_blend {
+  int32_t N, T, C, Cn, H, W;
+  const float* input; /* [N,T,C,H,W] */
+  int64_t in_sn, in_st, in_sc, in_sh;
+  const float* mask; /* [N,T,H,W] */
+  int64_t m_sn, m_st, m_sh;
+  const float* noise; /* [N,Cn,H,W]; NULL <=> Cn = 0 */
+  int64_t nz_sn, nz_sc, nz_sh;
+  float* out; /* [N,T,C,H,W] (forward) */
+  int64_t out_sn, out_st, out_sc, out_sh;
+  const float* grad_out; /* [N,T,C,H,W] (backward) */
+  int64_t go_sn, go_st, go_sc, go_sh;
+  float* grad_input; /* [N,T,C,H,W] or NULL */
+  int64_t gi_sn, gi_st, gi_sc, gi_sh;
+  float* grad_mask; /* [N,T,H,W] or NULL */
+  int64_t gm_sn, gm_st, gm_sh;
+  float* grad_noise; /* [N,Cn,H,W] or NULL */
+  int64_t gn_sn, gn_sc, gn_sh;
+} fwb_blend;
+
 /* Library version (FWB_VERSION of the build). */
 int32_t fwb_version(void);
 
@@ -137,6 +163,10 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream);
  * with spare store bandwidth, so the fused backward can be called with FWB_FLAG_GRAD_SRC_ZEROED and needs no memset
  * pass.  Planes the kernel cannot clear in place (unaligned / odd strides) are cleared by memsets on `stream`. */
 int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, void* stream);
+
+/* `refine`'s mask blend (utils/net_utils.py:141-143), see fwb_blend above. */
+int32_t fwb_mask_blend_forward(const fwb_blend* b, void* stream);
+int32_t fwb_mask_blend_backward(const fwb_blend* b, void* stream);
 
 /* Debug / parity: integer sample indices and validity bits of direction `d`.
  * x0,y0: int32 [N,T,H,W] contiguous; valid: uint8 [N,T,H,W], bit0 nw, bit1 ne, bit2 sw, bit3 se.
