@@ -364,6 +364,27 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     for name, fn in klist:
         kt[name] = timed(fn, ksteps, 3, sync) / ksteps
 
+    # ---- aux: `refine`'s mask blend (utils/net_utils.py:141-143) as one streaming kernel each way, T = 3 frames
+    aux = None
+    if args.aux:
+        Ta, Ca = 3, sum(CH)
+        a_in = torch.randn(cfg["N"], Ta, Ca, cfg["H"], cfg["W"], device=dev, requires_grad=True)
+        a_m = torch.rand(cfg["N"], Ta, cfg["H"], cfg["W"], device=dev, requires_grad=True)
+        a_nz = torch.randn(cfg["N"], 3, cfg["H"], cfg["W"], device=dev, requires_grad=True)
+        a_go = torch.randn_like(a_in)
+        a_out = P.mask_blend(a_in, a_m, a_nz)
+        pixf = cfg["N"] * Ta * cfg["H"] * cfg["W"]
+        t_f = timed(lambda: P.mask_blend(a_in, a_m, a_nz), 20, 3, sync) / 20
+        t_b = timed(lambda: torch.autograd.grad(a_out, (a_in, a_m, a_nz), a_go, retain_graph=True), 20, 3, sync) / 20
+        bf = pixf * (8 * Ca + 4) + cfg["N"] * cfg["H"] * cfg["W"] * 12          # in + out + mask (+ noise once per clip)
+        bb = pixf * (12 * Ca + 8) + cfg["N"] * cfg["H"] * cfg["W"] * 24        # go + in + gi, mask + gm (+ noise, gnoise)
+        pk = peaks()[0]
+        aux = {"mask_blend_forward": {"ms": t_f * 1e3, "GBps": bf / t_f / 1e9, "frac": bf / t_f / 1e9 / pk, "bytes": bf},
+               "mask_blend_backward": {"ms": t_b * 1e3, "GBps": bb / t_b / 1e9, "frac": bb / t_b / 1e9 / pk, "bytes": bb,
+                                       "note": "autograd.grad through the op (includes torch's allocation of the 3 gradients)"},
+               "shape": [cfg["N"], Ta, Ca, cfg["H"], cfg["W"]]}
+        del a_in, a_m, a_nz, a_go, a_out
+
     # ---- e2e: public API for HOST buffers (HostWarpBlend: the autograd op per batch chunk, pinned host in -> pinned host
     # out, H2D of every input and D2H of every output / gradient inside the timed region, copies overlapped with compute)
     host_in = [t.cpu().pin_memory() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]] + inp["gos"]]
@@ -410,6 +431,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
             "clocks": clocks,
         }
+        if aux:
+            out["aux_kernels"] = aux
         if world == 1 and not args.no_cpu:
             v, cores, reps = time_cpu_reference(cfg, cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1, 10.0, 3, 30)
             ns = cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1
@@ -441,6 +464,7 @@ def main():
                     help="who zero-fills grad_src before the fused backward: the forward kernel (default), the backward's "
                          "memsets, or a side stream (A/B)")
     ap.add_argument("--e2e-chunk", type=int, default=1, help="clips per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--aux", action="store_true", help="also time the mask-blend (refine) kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")
     args = ap.parse_args()

@@ -7,10 +7,10 @@ C-ABI (include/flowwarp_b200.h), exposed as a PyTorch autograd op.  No CPU / tor
 from .net_utils import (FlowWrapper, bidirectional_warp, blend_with_noise, warp, warp_back, warp_blend,
                         warp_multi)
 from .host_pipeline import HostWarpBlend, warp_blend_host
-from .ops import flow_warp_blend, sample_indices
+from .ops import flow_warp_blend, mask_blend, sample_indices
 
 __all__ = [
     "FlowWrapper", "warp", "warp_back", "warp_multi", "warp_blend", "bidirectional_warp", "blend_with_noise",
-    "flow_warp_blend", "sample_indices", "HostWarpBlend", "warp_blend_host",
+    "flow_warp_blend", "mask_blend", "sample_indices", "HostWarpBlend", "warp_blend_host",
 ]
 __version__ = "1.0.0"

@@ -655,10 +655,19 @@ int32_t fwb_mask_blend_backward(const fwb_blend* b, void* stream) {
   BlendP B;
   blend_params(b, B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (blend_vec_ok(b, true))
-    mask_blend_bwd_kernel<4, 4><<<dim3((b->W / 4 + 127) / 128, b->H, b->N), 128, 0, s>>>(B);
-  else
-    mask_blend_bwd_kernel<1, 4><<<dim3((b->W + 127) / 128, b->H, b->N), 128, 0, s>>>(B);
+  const bool vec = blend_vec_ok(b, true);
+  if (B.gi || B.gm || (B.gn && B.T == 1)) {
+    if (vec)
+      mask_blend_bwd_kernel<4><<<dim3((b->W / 4 + 127) / 128, b->H, b->N * b->T), 128, 0, s>>>(B);
+    else
+      mask_blend_bwd_kernel<1><<<dim3((b->W + 127) / 128, b->H, b->N * b->T), 128, 0, s>>>(B);
+  }
+  if (B.gn && B.T > 1 && B.Cn > 0) {
+    if (vec)
+      mask_blend_gnoise_kernel<4><<<dim3((b->W / 4 + 127) / 128, b->H, b->N * B.Cn), 128, 0, s>>>(B);
+    else
+      mask_blend_gnoise_kernel<1><<<dim3((b->W + 127) / 128, b->H, b->N * B.Cn), 128, 0, s>>>(B);
+  }
   return (int32_t)cudaGetLastError();
 }
 

@@ -88,65 +88,70 @@ __global__ void __launch_bounds__(128) mask_blend_fwd_kernel(const __grid_consta
   }
 }
 
-// backward: grid (ceil(W/V/128), H, N), 128 threads; a thread owns its pixels for every t and c, so
+// backward, kernel A: grid (ceil(W/V/128), H, N*T), 128 threads; a thread owns its pixels of one (n, t) for every c:
 //   grad_input[n,t,c] = g * mask[n,t]
-//   grad_mask[n,t]    = sum_c g * (input[n,t,c] - noise[n,c])       (accumulated in registers for t < TR, else RMW)
-//   grad_noise[n,c]   = sum_t g * (1 - mask[n,t])
-// need no cross-thread reduction and no atomics: deterministic.
-template <int V, int TR>
-__global__ void __launch_bounds__(128) mask_blend_bwd_kernel(const __grid_constant__ BlendP B) {
-  const int j = (blockIdx.x * 128 + threadIdx.x) * V, i = blockIdx.y, n = blockIdx.z;
+//   grad_mask[n,t]    = sum_c g * (input[n,t,c] - noise[n,c])      (register accumulator, fixed order: deterministic)
+//   grad_noise[n,c]   = g * (1 - mask[n,0])                        only when T == 1 (no sum over frames needed)
+template <int V>
+__global__ void __launch_bounds__(128, 8) mask_blend_bwd_kernel(const __grid_constant__ BlendP B) {
+  const int j = (blockIdx.x * 128 + threadIdx.x) * V, i = blockIdx.y;
   if (j >= B.W) return;
-  Vec<V> m[TR], gm[TR];
+  const int n = blockIdx.z / B.T, t = blockIdx.z - n * B.T;
+  const Vec<V> m = Vec<V>::ld_keep(B.m + n * B.m_sn + t * B.m_st + i * B.m_sh + j);
+  Vec<V> gm;
 #pragma unroll
-  for (int t = 0; t < TR; ++t) {
-    if (t < B.T) m[t] = Vec<V>::ld_keep(B.m + n * B.m_sn + t * B.m_st + i * B.m_sh + j);
-#pragma unroll
-    for (int k = 0; k < V; ++k) gm[t].v[k] = 0.f;
-  }
-  const bool want_gm = B.gm != nullptr, want_gi = B.gi != nullptr;
+  for (int k = 0; k < V; ++k) gm.v[k] = 0.f;
+  const bool want_gm = B.gm != nullptr, want_gi = B.gi != nullptr, want_gn = B.gn != nullptr && B.T == 1;
+  const float* gp = B.go + n * B.go_sn + t * B.go_st + i * B.go_sh + j;
+  const float* ip = B.in + n * B.in_sn + t * B.in_st + i * B.in_sh + j;
+  float* gip = want_gi ? B.gi + n * B.gi_sn + t * B.gi_st + i * B.gi_sh + j : nullptr;
+#pragma unroll 2
   for (int c = 0; c < B.C; ++c) {
-    const bool has_nz = c < B.Cn;
-    Vec<V> z, gz;
+    const Vec<V> g = Vec<V>::ld(gp + c * B.go_sc);
+    if (want_gi) {
+      Vec<V> r;
 #pragma unroll
-    for (int k = 0; k < V; ++k) z.v[k] = gz.v[k] = 0.f;
-    if (has_nz && want_gm) z = Vec<V>::ld_keep(B.nz + n * B.nz_sn + c * B.nz_sc + i * B.nz_sh + j);
-    // one (t, c) item; `acc` is the register accumulator of grad_mask[t] or NULL (read-modify-write in memory)
-    auto item = [&](int t, const Vec<V>& mt, Vec<V>* acc) {
-      const Vec<V> g = Vec<V>::ld(B.go + n * B.go_sn + t * B.go_st + c * B.go_sc + i * B.go_sh + j);
-      if (want_gi) {
-        Vec<V> r;
+      for (int k = 0; k < V; ++k) r.v[k] = __fmul_rn(g.v[k], m.v[k]);
+      r.st(gip + c * B.gi_sc);
+    }
+    if (want_gm) {
+      const Vec<V> x = Vec<V>::ld(ip + c * B.in_sc);
+      if (c < B.Cn) {
+        const Vec<V> z = Vec<V>::ld_keep(B.nz + n * B.nz_sn + c * B.nz_sc + i * B.nz_sh + j);
 #pragma unroll
-        for (int k = 0; k < V; ++k) r.v[k] = __fmul_rn(g.v[k], mt.v[k]);
-        r.st(B.gi + n * B.gi_sn + t * B.gi_st + c * B.gi_sc + i * B.gi_sh + j);
+        for (int k = 0; k < V; ++k) gm.v[k] = fmaf(g.v[k], x.v[k] - z.v[k], gm.v[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) gm.v[k] = fmaf(g.v[k], x.v[k], gm.v[k]);
       }
-      if (want_gm) {
-        const Vec<V> x = Vec<V>::ld(B.in + n * B.in_sn + t * B.in_st + c * B.in_sc + i * B.in_sh + j);
-        if (acc) {
+    }
+    if (want_gn && c < B.Cn) {
+      Vec<V> r;
 #pragma unroll
-          for (int k = 0; k < V; ++k) acc->v[k] = fmaf(g.v[k], x.v[k] - z.v[k], acc->v[k]);
-        } else {  // more frames than register accumulators: read-modify-write of this thread's own grad_mask cells
-          float* p = B.gm + n * B.gm_sn + t * B.gm_st + i * B.gm_sh + j;
-#pragma unroll
-          for (int k = 0; k < V; ++k) p[k] = fmaf(g.v[k], x.v[k] - z.v[k], c == 0 ? 0.f : p[k]);
-        }
-      }
-      if (has_nz) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) gz.v[k] = fmaf(g.v[k], 1.0f - mt.v[k], gz.v[k]);
-      }
-    };
-#pragma unroll
-    for (int t = 0; t < TR; ++t)
-      if (t < B.T) item(t, m[t], &gm[t]);
-    for (int t = TR; t < B.T; ++t) item(t, Vec<V>::ld_keep(B.m + n * B.m_sn + t * B.m_st + i * B.m_sh + j), nullptr);
-    if (has_nz && B.gn) gz.st(B.gn + n * B.gn_sn + c * B.gn_sc + i * B.gn_sh + j);
+      for (int k = 0; k < V; ++k) r.v[k] = g.v[k] * (1.0f - m.v[k]);
+      r.st(B.gn + n * B.gn_sn + c * B.gn_sc + i * B.gn_sh + j);
+    }
   }
-  if (want_gm) {
+  if (want_gm) gm.st(B.gm + n * B.gm_sn + t * B.gm_st + i * B.gm_sh + j);
+}
+
+// backward, kernel B (T > 1 only): grad_noise[n,c] = sum_t g[n,t,c] * (1 - mask[n,t]) for the Cn noise channels;
+// grid (ceil(W/V/128), H, N*Cn).  Re-reads Cn of the C grad_out planes (3 of 23 on the path) and the masks.
+template <int V>
+__global__ void __launch_bounds__(128, 8) mask_blend_gnoise_kernel(const __grid_constant__ BlendP B) {
+  const int j = (blockIdx.x * 128 + threadIdx.x) * V, i = blockIdx.y;
+  if (j >= B.W) return;
+  const int n = blockIdx.z / B.Cn, c = blockIdx.z - n * B.Cn;
+  Vec<V> acc;
 #pragma unroll
-    for (int t = 0; t < TR; ++t)
-      if (t < B.T) gm[t].st(B.gm + n * B.gm_sn + t * B.gm_st + i * B.gm_sh + j);
+  for (int k = 0; k < V; ++k) acc.v[k] = 0.f;
+  for (int t = 0; t < B.T; ++t) {
+    const Vec<V> g = Vec<V>::ld_keep(B.go + n * B.go_sn + t * B.go_st + c * B.go_sc + i * B.go_sh + j);
+    const Vec<V> m = Vec<V>::ld_keep(B.m + n * B.m_sn + t * B.m_st + i * B.m_sh + j);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc.v[k] = fmaf(g.v[k], 1.0f - m.v[k], acc.v[k]);
   }
+  acc.st(B.gn + n * B.gn_sn + c * B.gn_sc + i * B.gn_sh + j);
 }
 
 static inline bool blend_vec_ok(const fwb_blend* b, bool bwd) {
@@ -170,7 +175,7 @@ static inline bool blend_vec_ok(const fwb_blend* b, bool bwd) {
 static inline int blend_validate(const fwb_blend* b, bool bwd) {
   if (!b) return FWB_E_NULL;
   if (b->N < 0 || b->T < 1 || b->C < 1 || b->H < 1 || b->W < 1 || b->Cn < 0 || b->Cn > b->C) return FWB_E_SHAPE;
-  if (b->H > 65535 || (long long)b->N * b->T > 65535) return FWB_E_RANGE;
+  if (b->H > 65535 || (long long)b->N * b->T > 65535 || (long long)b->N * b->Cn > 65535) return FWB_E_RANGE;
   if (!b->input || !b->mask || (b->Cn > 0 && !b->noise)) return FWB_E_NULL;
   if (!bwd && !b->out) return FWB_E_NULL;
   if (bwd && !b->grad_out) return FWB_E_NULL;

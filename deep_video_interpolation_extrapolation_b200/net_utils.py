@@ -25,7 +25,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .ops import flow_warp_blend
+from .ops import flow_warp_blend, mask_blend
 
 Tensor = torch.Tensor
 
@@ -88,11 +88,11 @@ def warp_multi(frames: Sequence[Tensor], flow: Tensor, opt, flowwarpper, mask: T
 
 
 def blend_with_noise(input: Tensor, mask: Tensor, noise: Tensor) -> Tensor:
-    """utils/net_utils.py:141-143 (the blend in `refine`): input[:,i]*mask[:,i:i+1] + noise*(1-mask[:,i:i+1]).
-
-    Pointwise on the op's output; kept in torch (it is 3 of ~900 B/pixel and not part of the warp)."""
-    m = mask.unsqueeze(2)
-    return input * m + noise.unsqueeze(1) * (1.0 - m)
+    """utils/net_utils.py:141-143 (the blend in `refine`): input[:,i]*mask[:,i:i+1] + noise*(1-mask[:,i:i+1]) for
+    every frame i, as ONE streaming kernel (`ops.mask_blend`: the four pointwise torch kernels per frame and the
+    Python loop are gone).  `noise` may carry fewer channels than `input` (the RGB noise of `refine`): the remaining
+    channels blend against zero, which replaces the `cat([noise_bg, zeros(bs,20,h,w)])` of :134-136."""
+    return mask_blend(input, mask, noise)
 
 
 def bidirectional_warp(

@@ -318,6 +318,96 @@ def flow_warp_blend(
     return outs
 
 
+def _fill_blend(inp: Tensor, mask: Tensor, noise: Optional[Tensor]) -> "L.fwb_blend":
+    b = L.fwb_blend()
+    N, T, C, H, W = inp.shape
+    b.N, b.T, b.C, b.H, b.W = N, T, C, H, W
+    b.Cn = 0 if noise is None else noise.shape[1]
+    b.input = inp.data_ptr()
+    b.in_sn, b.in_st, b.in_sc, b.in_sh = inp.stride()[:4]
+    b.mask = mask.data_ptr()
+    b.m_sn, b.m_st, b.m_sh = mask.stride()[:3]
+    if noise is not None:
+        b.noise = noise.data_ptr()
+        b.nz_sn, b.nz_sc, b.nz_sh = noise.stride()[:3]
+    return b
+
+
+class _MaskBlendFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp: Tensor, mask: Tensor, noise: Optional[Tensor]):
+        inp, mask, noise = _wcontig(inp), _wcontig(mask), _wcontig(noise)
+        out = torch.empty(inp.shape, dtype=torch.float32, device=inp.device)
+        lib = L.load()
+        with torch.cuda.device(inp.device):
+            b = _fill_blend(inp, mask, noise)
+            b.out = out.data_ptr()
+            b.out_sn, b.out_st, b.out_sc, b.out_sh = out.stride()[:4]
+            L.check(lib.fwb_mask_blend_forward(ctypes.byref(b), _stream_ptr(inp.device)), "fwb_mask_blend_forward")
+        ctx.save_for_backward(inp, mask, noise)
+        return out
+
+    @staticmethod
+    def backward(ctx, go: Tensor):
+        inp, mask, noise = ctx.saved_tensors
+        go = _wcontig(go)
+        f32 = dict(dtype=torch.float32, device=inp.device)
+        gi = torch.empty(inp.shape, **f32) if ctx.needs_input_grad[0] else None
+        gm = torch.empty(mask.shape, **f32) if ctx.needs_input_grad[1] else None
+        gn = torch.empty(noise.shape, **f32) if (noise is not None and ctx.needs_input_grad[2]) else None
+        lib = L.load()
+        with torch.cuda.device(inp.device):
+            b = _fill_blend(inp, mask, noise)
+            b.grad_out = go.data_ptr()
+            b.go_sn, b.go_st, b.go_sc, b.go_sh = go.stride()[:4]
+            if gi is not None:
+                b.grad_input = gi.data_ptr()
+                b.gi_sn, b.gi_st, b.gi_sc, b.gi_sh = gi.stride()[:4]
+            if gm is not None:
+                b.grad_mask = gm.data_ptr()
+                b.gm_sn, b.gm_st, b.gm_sh = gm.stride()[:3]
+            if gn is not None:
+                b.grad_noise = gn.data_ptr()
+                b.gn_sn, b.gn_sc, b.gn_sh = gn.stride()[:3]
+            L.check(lib.fwb_mask_blend_backward(ctypes.byref(b), _stream_ptr(inp.device)), "fwb_mask_blend_backward")
+        return gi, gm, gn
+
+
+def mask_blend(input: Tensor, mask: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+    """out[:, i] = input[:, i] * mask[:, i:i+1] + noise * (1 - mask[:, i:i+1])   (utils/net_utils.py:141-143)
+
+    input [N,T,C,H,W]; mask [N,T,H,W]; noise [N,Cn,H,W] with Cn <= C or None: channels without a noise plane blend
+    against zero, which is what `refine` builds with `torch.cat([noise_bg, zeros(bs, 20, h, w)])` when opt.seg
+    (utils/net_utils.py:134-136).  One streaming kernel forward, one backward; bit-identical to the torch expression.
+    """
+    every = [t for t in (input, mask, noise) if t is not None]
+    for t in every:
+        if not isinstance(t, Tensor):
+            raise TypeError("mask_blend: tensors expected")
+        if not t.is_cuda:
+            raise RuntimeError("mask_blend: CUDA tensors required (this library has no CPU path)")
+        if t.device != input.device:
+            raise RuntimeError(f"mask_blend: all tensors must be on {input.device}, got {t.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"mask_blend: float32 required, got {t.dtype}")
+    if input.dim() != 5:
+        raise RuntimeError(f"mask_blend: input must be [N,T,C,H,W], got {tuple(input.shape)}")
+    N, T, C, H, W = input.shape
+    if H < 1 or W < 1 or C < 1 or T < 1:
+        raise RuntimeError("mask_blend: non-empty T, C and spatial dims required")
+    if mask.dim() != 4 or mask.shape[0] != N or mask.shape[1] < T or tuple(mask.shape[2:]) != (H, W):
+        raise RuntimeError(f"mask_blend: mask must be [N,T>={T},H,W], got {tuple(mask.shape)}")
+    mask = mask[:, :T]
+    if noise is not None:
+        if noise.dim() != 4 or noise.shape[0] != N or noise.shape[1] > C or tuple(noise.shape[2:]) != (H, W):
+            raise RuntimeError(f"mask_blend: noise must be [N,Cn<={C},H,W], got {tuple(noise.shape)}")
+        if noise.shape[1] == 0:
+            noise = None
+    if N == 0:
+        return input.new_empty(input.shape)
+    return _MaskBlendFn.apply(input, mask, noise)
+
+
 def sample_indices(flow: Tensor, gate: Optional[Tensor] = None, sign: float = -1.0,
                    padding_mode: str = "zeros", align_corners: bool = False):
     """Debug / parity: (x0, y0, valid_bits, ix, iy) the kernels use for `flow` [N,2,H,W] or [N,2,T,H,W].

@@ -173,3 +173,39 @@ def sample_indices(flow, gate=None, sign=-1.0, padding_mode="zeros", align_corne
     if rc:
         raise ValueError(f"oracle sample_indices: code {rc}")
     return x0, y0, valid, ix, iy
+
+
+# ---------------------------------------------------------------------------------------------
+# `refine`'s mask blend (utils/net_utils.py:131-143), numpy, same op order as the torch expression at :141-142:
+#     input[:, i] * mask[:, i:i+1] + noise * (1. - mask[:, i:i+1])
+# with noise = cat([noise_bg, zeros(bs, 20, h, w)], 1) when opt.seg (:134-136).  fp32 ops, one rounding each.
+# ---------------------------------------------------------------------------------------------
+def mask_blend_forward(inp, mask, noise_bg=None) -> np.ndarray:
+    """inp [N,T,C,H,W], mask [N,T,H,W], noise_bg [N,Cn<=C,H,W] or None -> [N,T,C,H,W] (float32)."""
+    inp, mask = _f32(inp), _f32(mask)
+    N, T, C, H, W = inp.shape
+    noise = np.zeros((N, C, H, W), np.float32)
+    if noise_bg is not None:
+        nb = _f32(noise_bg)
+        noise[:, :nb.shape[1]] = nb  # :134-136 (torch.cat with a zero block)
+    out = np.empty_like(inp)
+    one = np.float32(1.0)
+    for i in range(T):  # :141 the Python loop over opt.vid_length
+        m = mask[:, i:i + 1]
+        out[:, i] = inp[:, i] * m + noise * (one - m)
+    return out
+
+
+def mask_blend_backward(inp, mask, noise_bg, grad_out):
+    """float64 gradients of mask_blend_forward w.r.t. (inp, mask, noise_bg)."""
+    inp, mask, g = np.asarray(inp, np.float64), np.asarray(mask, np.float64), np.asarray(grad_out, np.float64)
+    N, T, C, H, W = inp.shape
+    noise = np.zeros((N, C, H, W), np.float64)
+    Cn = 0
+    if noise_bg is not None:
+        Cn = noise_bg.shape[1]
+        noise[:, :Cn] = noise_bg
+    gi = g * mask[:, :, None]
+    gm = (g * (inp - noise[:, None])).sum(axis=2)
+    gn = (g * (1.0 - mask[:, :, None])).sum(axis=1)[:, :Cn]
+    return gi, gm, gn

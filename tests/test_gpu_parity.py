@@ -554,3 +554,70 @@ def test_backward_twice_and_prezero_switch(pkg, monkeypatch):
     c = run(False)
     for x, y, z in zip(a, b, c):
         assert relerr(y, x) <= BWD_TOL and relerr(z, x) <= BWD_TOL
+
+
+# ---------------------------------------------------------------- refine's mask blend (utils/net_utils.py:131-143)
+@pytest.mark.parametrize("shape,Cn", [((2, 3, 23, 32, 64), 3), ((1, 1, 3, 17, 30), 3), ((2, 6, 5, 16, 36), 0),
+                                      ((1, 2, 23, 9, 7), 23)])
+def test_mask_blend_bit_exact_vs_torch_and_oracle(pkg, oracle, shape, Cn):
+    """out = input*mask + noise*(1-mask) per frame: bit-identical to the reference's torch expression (same device)
+    and to the numpy oracle; gradients vs fp64 oracle at 1e-5.  Covers W % 4 != 0 (scalar path), T above the register
+    accumulators (6 > 4: read-modify-write path), no noise, full-channel noise."""
+    N, T, C, H, W = shape
+    rng = np.random.default_rng(7)
+    inp = rng.standard_normal(shape).astype(np.float32)
+    mask = synth.mask(3, N, H, W, T=T)
+    noise = rng.standard_normal((N, Cn, H, W)).astype(np.float32) if Cn else None
+    go = rng.standard_normal(shape).astype(np.float32)
+    ti, tm = cu(inp, True), cu(mask, True)
+    tn = cu(noise, True) if Cn else None
+    out = pkg.mask_blend(ti, tm, tn)
+    # the reference expression, on the same device (utils/net_utils.py:134-136,141-142)
+    full = torch.cat([tn.detach(), torch.zeros(N, C - Cn, H, W, device="cuda")], 1) if Cn else torch.zeros(N, C, H, W, device="cuda")
+    ref = torch.stack([ti.detach()[:, i] * tm.detach()[:, i:i + 1] + full * (1. - tm.detach()[:, i:i + 1]) for i in range(T)], 1)
+    assert torch.equal(out, ref)
+    assert np.array_equal(out.detach().cpu().numpy(), oracle.mask_blend_forward(inp, mask, noise))
+    out.backward(cu(go))
+    gi, gm, gn = oracle.mask_blend_backward(inp, mask, noise, go)
+    assert relerr(ti.grad, gi) <= BWD_TOL
+    assert relerr(tm.grad, gm) <= BWD_TOL
+    if Cn:
+        assert relerr(tn.grad, gn) <= BWD_TOL
+    # drop-in name of the reference's blend
+    assert torch.equal(pkg.blend_with_noise(ti.detach(), tm.detach(), tn.detach() if Cn else None), ref)
+
+
+def test_mask_blend_strided_views_and_errors(pkg):
+    N, T, C, H, W = 2, 2, 4, 8, 16
+    big = torch.randn(N, T, C + 2, H, W + 4, device="cuda")
+    inp = big[:, :, 1:C + 1, :, 4:]            # strided view, 16-byte aligned rows
+    mask = torch.rand(N, T + 1, H, W, device="cuda")  # more frames than input: the first T are used
+    noise = torch.randn(N, 3, H, W, device="cuda")
+    out = pkg.mask_blend(inp, mask, noise)
+    full = torch.cat([noise, torch.zeros(N, C - 3, H, W, device="cuda")], 1)
+    ref = torch.stack([inp[:, i] * mask[:, i:i + 1] + full * (1. - mask[:, i:i + 1]) for i in range(T)], 1)
+    assert torch.equal(out, ref)
+    with pytest.raises(RuntimeError):
+        pkg.mask_blend(inp.cpu(), mask, noise)
+    with pytest.raises(RuntimeError):
+        pkg.mask_blend(inp, mask[:, :1], noise)
+    with pytest.raises(RuntimeError):
+        pkg.mask_blend(inp, mask, torch.randn(N, C + 1, H, W, device="cuda"))
+    assert pkg.mask_blend(inp[:0], mask[:0], noise[:0]).shape[0] == 0
+
+
+@pytest.mark.parametrize("name", ["refine_0.npz", "refine_1.npz"])
+def test_mask_blend_vs_reference_refine_golden(pkg, golden_dir, name):
+    """blend_with_noise against the committed outputs of the unmodified reference `refine` (identity refine_net)."""
+    z = np.load(os.path.join(golden_dir, name))
+    N, T, C, H, W = z["shape"]
+    s = z["seeds"]
+    ti = cu(synth.grad(s[0], (N, T, C, H, W)), True)
+    tm = cu(synth.mask(s[1], N, H, W, T=T), True)
+    tn = cu(synth.rgb(s[2], N, H, W, 3), True)
+    out = pkg.blend_with_noise(ti, tm, tn)
+    assert np.array_equal(out.detach().cpu().numpy(), z["out"])  # bit-exact
+    out.backward(cu(synth.grad(s[3], (N, T, C, H, W))))
+    assert relerr(ti.grad, z["grad_input"]) <= BWD_TOL
+    assert relerr(tm.grad, z["grad_mask"]) <= BWD_TOL
+    assert relerr(tn.grad, z["grad_noise"]) <= BWD_TOL

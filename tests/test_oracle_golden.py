@@ -108,3 +108,18 @@ def test_config1_clip_golden(oracle, golden_dir):
         assert relerr(o[..., ::4, ::4], z[name]) <= FWD_TOL, name
         ssum = o.astype(np.float64).sum((0, 1, 3, 4))
         assert np.abs(ssum - z[name + "_sum"]).max() <= 1e-6 * np.abs(o).sum() / o.shape[2], name
+
+
+@pytest.mark.parametrize("name", ["refine_0.npz", "refine_1.npz"])
+def test_refine_blend_golden(oracle, golden_dir, name):
+    """oracle.mask_blend_* against the unmodified reference `refine` (identity refine_net), utils/net_utils.py:131-150."""
+    z = np.load(os.path.join(golden_dir, name))
+    N, T, C, H, W = z["shape"]
+    s = z["seeds"]
+    inp, mask, noise = synth.grad(s[0], (N, T, C, H, W)), synth.mask(s[1], N, H, W, T=T), synth.rgb(s[2], N, H, W, 3)
+    go = synth.grad(s[3], (N, T, C, H, W))
+    assert np.array_equal(oracle.mask_blend_forward(inp, mask, noise), z["out"])  # bit-exact
+    gi, gm, gn = oracle.mask_blend_backward(inp, mask, noise, go)
+    assert relerr(gi, z["grad_input"]) <= BWD_TOL
+    assert relerr(gm, z["grad_mask"]) <= BWD_TOL
+    assert relerr(gn, z["grad_noise"]) <= BWD_TOL
