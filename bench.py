@@ -385,6 +385,33 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
                "shape": [cfg["N"], Ta, Ca, cfg["H"], cfg["W"]]}
         del a_in, a_m, a_nz, a_go, a_out
 
+    # ---- variant (reported separately, different algorithmic bytes): segmentation given as uint8 label maps
+    variants = None
+    if args.aux:
+        K = CH[1]
+        lab0 = inp["f0"][1].argmax(1).to(torch.uint8)
+        lab1 = inp["f1"][1].argmax(1).to(torch.uint8)
+        lv = [t.detach().clone().requires_grad_() for t in (inp["f0"][0], inp["f1"][0], inp["ff"], inp["fb"], inp["mf"], inp["mb"])]
+
+        def label_step():
+            outs = P.warp_blend_labels([lv[0]], [lv[1]], lab0, lab1, K, lv[2], lv[3], lv[4], lv[5])
+            torch.autograd.backward(outs, inp["gos"])
+            for t in lv:
+                t.grad = None
+
+        t_l = timed(label_step, 20, 3, sync) / 20
+        pix = cfg["N"] * cfg["H"] * cfg["W"]
+        c3 = CH[0]
+        # fwd: R 2 rgb frames 8*c3, 2 label maps 2, flows 16, masks 8, W out 4*(c3+K); bwd: R gout 4*(c3+K), rgb 8*c3, labels 2,
+        # flows 16, masks 8, W grad rgb 8*c3, gflows 16, gmasks 8
+        lb = (8 * c3 + 2 + 24 + 4 * (c3 + K)) + (4 * (c3 + K) + 8 * c3 + 2 + 24 + 8 * c3 + 24)
+        variants = {"compact_seg_labels": {"ms_per_step": t_l * 1e3, "Gpix_per_s": pix / t_l / 1e9, "bytes_per_pixel": lb,
+                                           "GBps": pix * lb / t_l / 1e9, "frac": pix * lb / t_l / 1e9 / peaks()[0],
+                                           "api": "warp_blend_labels + autograd.backward (RGB dense kernels + label kernels; "
+                                                  "autograd sums the two flow / mask gradients)",
+                                           "note": "seg as uint8 labels (SURVEY 8f row 4): same outputs as the dense op on one-hot "
+                                                   "maps, no seg source gradient; NOT the headline metric"}}
+
     # ---- e2e: public API for HOST buffers (HostWarpBlend: the autograd op per batch chunk, pinned host in -> pinned host
     # out, H2D of every input and D2H of every output / gradient inside the timed region, copies overlapped with compute)
     host_in = [t.cpu().pin_memory() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]] + inp["gos"]]
@@ -433,6 +460,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
         }
         if aux:
             out["aux_kernels"] = aux
+        if variants:
+            out["variants"] = variants
         if world == 1 and not args.no_cpu:
             v, cores, reps = time_cpu_reference(cfg, cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1, 10.0, 3, 30)
             ns = cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1

@@ -5,12 +5,12 @@ A drop-in for ONE hot path of lzhangbj/deep_video_interpolation_extrapolation
 C-ABI (include/flowwarp_b200.h), exposed as a PyTorch autograd op.  No CPU / torch fallback.
 """
 from .net_utils import (FlowWrapper, bidirectional_warp, blend_with_noise, warp, warp_back, warp_blend,
-                        warp_multi)
+                        warp_blend_labels, warp_multi)
 from .host_pipeline import HostWarpBlend, warp_blend_host
-from .ops import flow_warp_blend, mask_blend, sample_indices
+from .ops import flow_warp_blend, label_warp_blend, mask_blend, sample_indices
 
 __all__ = [
     "FlowWrapper", "warp", "warp_back", "warp_multi", "warp_blend", "bidirectional_warp", "blend_with_noise",
-    "flow_warp_blend", "mask_blend", "sample_indices", "HostWarpBlend", "warp_blend_host",
+    "flow_warp_blend", "label_warp_blend", "warp_blend_labels", "mask_blend", "sample_indices", "HostWarpBlend", "warp_blend_host",
 ]
 __version__ = "1.0.0"

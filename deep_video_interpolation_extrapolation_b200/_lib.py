@@ -81,6 +81,21 @@ class fwb_blend(C.Structure):
     ]
 
 
+class fwb_label_problem(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("n_dirs", C.c_int32), ("K", C.c_int32), ("padding_mode", C.c_int32), ("align_corners", C.c_int32),
+        ("dir", fwb_dir * 2),
+        ("labels", C.c_void_p * 2), ("lab_sn", i64 * 2), ("lab_st", i64 * 2), ("lab_sh", i64 * 2),
+        ("out", C.c_void_p), ("out_sn", i64), ("out_st", i64), ("out_sc", i64), ("out_sh", i64),
+        ("grad_out", C.c_void_p), ("go_sn", i64), ("go_st", i64), ("go_sc", i64), ("go_sh", i64),
+        ("grad_flow", C.c_void_p * 2), ("gf_sn", i64 * 2), ("gf_sc", i64 * 2), ("gf_st", i64 * 2), ("gf_sh", i64 * 2),
+        ("grad_gate", C.c_void_p * 2), ("gg_sn", i64 * 2), ("gg_st", i64 * 2), ("gg_sh", i64 * 2),
+        ("grad_blend", C.c_void_p * 2), ("gb_sn", i64 * 2), ("gb_st", i64 * 2), ("gb_sh", i64 * 2),
+        ("accumulate", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 LIB_NAME = "libflowwarp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
@@ -90,6 +105,8 @@ SYMBOLS = (
     "fwb_strerror",
     "fwb_warp_blend_forward",
     "fwb_warp_blend_forward_zero",
+    "fwb_label_warp_blend_forward",
+    "fwb_label_warp_blend_backward",
     "fwb_mask_blend_forward",
     "fwb_mask_blend_backward",
     "fwb_sample_indices",
@@ -125,6 +142,11 @@ def load() -> C.CDLL:
     lib.fwb_warp_blend_forward.argtypes = [pp, vp]
     lib.fwb_warp_blend_forward_zero.restype = C.c_int32
     lib.fwb_warp_blend_forward_zero.argtypes = [pp, gp, vp]
+    lp = C.POINTER(fwb_label_problem)
+    lib.fwb_label_warp_blend_forward.restype = C.c_int32
+    lib.fwb_label_warp_blend_forward.argtypes = [lp, vp]
+    lib.fwb_label_warp_blend_backward.restype = C.c_int32
+    lib.fwb_label_warp_blend_backward.argtypes = [lp, vp]
     bp = C.POINTER(fwb_blend)
     lib.fwb_mask_blend_forward.restype = C.c_int32
     lib.fwb_mask_blend_forward.argtypes = [bp, vp]

@@ -20,6 +20,7 @@
 #include "fwb_csr.cuh"
 #include "fwb_tile.cuh"
 #include "fwb_blend.cuh"
+#include "fwb_label.cuh"
 
 namespace fwb {
 
@@ -632,6 +633,84 @@ int32_t fwb_warp_blend_forward(const fwb_problem* p, void* stream) { return run_
 int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, void* stream) {
   if (!g) return FWB_E_NULL;
   return run_forward(p, g, stream);
+}
+
+static int label_params(const fwb_label_problem* p, bool bwd, LabelP& L) {
+  if (!p) return FWB_E_NULL;
+  if (p->N < 0 || p->T < 1 || p->H < 1 || p->W < 1 || p->K < 1 || p->K > 256) return FWB_E_SHAPE;
+  if ((long long)p->N * p->T > 65535) return FWB_E_SHAPE;
+  if (p->H > 32767 || p->W > 32767) return FWB_E_RANGE;
+  if (p->n_dirs < 1 || p->n_dirs > 2) return FWB_E_DIRS;
+  if (p->padding_mode != FWB_PAD_ZEROS && p->padding_mode != FWB_PAD_BORDER) return FWB_E_MODE;
+  if (p->align_corners != 0 && p->align_corners != 1) return FWB_E_MODE;
+  fwb_problem q;
+  memset(&q, 0, sizeof(q));
+  q.N = p->N, q.T = p->T, q.H = p->H, q.W = p->W, q.n_dirs = p->n_dirs, q.n_groups = 1;
+  q.padding_mode = p->padding_mode, q.align_corners = p->align_corners;
+  for (int d = 0; d < p->n_dirs; ++d) {
+    if (!p->dir[d].flow || !p->labels[d]) return FWB_E_NULL;
+    if (p->dir[d].sign != 1.0f && p->dir[d].sign != -1.0f) return FWB_E_MODE;
+    if (((uintptr_t)p->dir[d].flow | (uintptr_t)p->dir[d].gate | (uintptr_t)p->dir[d].blend) & 3u) return FWB_E_ALIGN;
+    if (p->lab_sh[d] < 0 || (long long)(p->H + 2) * p->lab_sh[d] > 2147483647LL) return FWB_E_SHAPE;
+    q.dir[d] = p->dir[d];
+  }
+  Params P;
+  to_params(&q, P);
+  L.geo = P.geo;
+  L.K = p->K;
+  for (int d = 0; d < 2; ++d) {
+    const int e = d < p->n_dirs ? d : 0;
+    L.dir[d] = P.dir[d];
+    L.lab[d] = p->labels[e];
+    L.lab_sn[d] = p->lab_sn[e], L.lab_st[d] = p->lab_st[e], L.lab_sh[d] = (int)p->lab_sh[e];
+    const bool on = d < p->n_dirs;
+    L.grad_flow[d] = on ? p->grad_flow[d] : nullptr;
+    L.gf_sn[d] = p->gf_sn[d], L.gf_sc[d] = p->gf_sc[d], L.gf_st[d] = p->gf_st[d], L.gf_sh[d] = p->gf_sh[d];
+    L.grad_gate[d] = on ? p->grad_gate[d] : nullptr;
+    L.gg_sn[d] = p->gg_sn[d], L.gg_st[d] = p->gg_st[d], L.gg_sh[d] = p->gg_sh[d];
+    L.grad_blend[d] = on ? p->grad_blend[d] : nullptr;
+    L.gb_sn[d] = p->gb_sn[d], L.gb_st[d] = p->gb_st[d], L.gb_sh[d] = p->gb_sh[d];
+    if (((uintptr_t)L.grad_flow[d] | (uintptr_t)L.grad_gate[d] | (uintptr_t)L.grad_blend[d]) & 3u) return FWB_E_ALIGN;
+  }
+  L.out = p->out, L.out_sn = p->out_sn, L.out_st = p->out_st, L.out_sc = (int)p->out_sc, L.out_sh = (int)p->out_sh;
+  L.go = p->grad_out, L.go_sn = p->go_sn, L.go_st = p->go_st, L.go_sc = (int)p->go_sc, L.go_sh = (int)p->go_sh;
+  L.accumulate = p->accumulate;
+  if (!bwd) {
+    if (!p->out) return FWB_E_NULL;
+    if ((uintptr_t)p->out & 3u) return FWB_E_ALIGN;
+    if (p->out_sc < 0 || p->out_sh < 0 || (long long)p->K * p->out_sc + (long long)(p->H + 2) * p->out_sh > 2147483647LL) return FWB_E_SHAPE;
+  } else {
+    if (!p->grad_out) return FWB_E_NULL;
+    if ((uintptr_t)p->grad_out & 3u) return FWB_E_ALIGN;
+    if (p->go_sc < 0 || p->go_sh < 0 || (long long)p->K * p->go_sc + (long long)(p->H + 2) * p->go_sh > 2147483647LL) return FWB_E_SHAPE;
+  }
+  return 0;
+}
+
+int32_t fwb_label_warp_blend_forward(const fwb_label_problem* p, void* stream) {
+  LabelP L;
+  int rc = label_params(p, false, L);
+  if (rc) return rc;
+  if (p->N == 0) return 0;
+  const dim3 grid((p->W + 31) / 32, (p->H + 7) / 8, p->N * p->T);
+  if (p->n_dirs == 2)
+    label_fwd_kernel<2><<<grid, LB_THREADS, 0, (cudaStream_t)stream>>>(L);
+  else
+    label_fwd_kernel<1><<<grid, LB_THREADS, 0, (cudaStream_t)stream>>>(L);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_label_warp_blend_backward(const fwb_label_problem* p, void* stream) {
+  LabelP L;
+  int rc = label_params(p, true, L);
+  if (rc) return rc;
+  if (p->N == 0) return 0;
+  const dim3 grid((p->W + 31) / 32, (p->H + 7) / 8, p->N * p->T);
+  if (p->n_dirs == 2)
+    label_bwd_kernel<2><<<grid, LB_THREADS, 0, (cudaStream_t)stream>>>(L);
+  else
+    label_bwd_kernel<1><<<grid, LB_THREADS, 0, (cudaStream_t)stream>>>(L);
+  return (int32_t)cudaGetLastError();
 }
 
 int32_t fwb_mask_blend_forward(const fwb_blend* b, void* stream) {

@@ -25,7 +25,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .ops import flow_warp_blend, mask_blend
+from .ops import flow_warp_blend, label_warp_blend, mask_blend
 
 Tensor = torch.Tensor
 
@@ -130,3 +130,19 @@ def warp_blend(
     return flow_warp_blend([(a, b) for a, b in zip(frames0, frames1)], [for_flow, back_flow],
                            blends=[for_mask, back_mask], signs=[-1.0, +1.0], padding_mode=padding_mode,
                            align_corners=align_corners, deterministic=deterministic)
+
+
+def warp_blend_labels(
+    frames0: Sequence[Tensor], frames1: Sequence[Tensor], labels0: Tensor, labels1: Tensor, num_classes: int,
+    for_flow: Tensor, back_flow: Tensor, for_mask: Tensor, back_mask: Tensor, padding_mode: str = "border",
+    align_corners: bool = False, deterministic: bool = False,
+) -> List[Tensor]:
+    """`warp_blend` with the segmentation maps given as uint8 label maps [N,H,W] instead of one-hot float tensors
+    (the compact format of SURVEY §8f row 4): returns [*blended float groups, blended seg [N,K,H,W]], the last entry
+    bit-identical to `warp_blend([one_hot(labels0)], [one_hot(labels1)], ...)`.  The float groups (RGB) go through the
+    dense kernels, the label maps through the label kernels; autograd sums their flow / mask gradients."""
+    outs = warp_blend(frames0, frames1, for_flow, back_flow, for_mask, back_mask, padding_mode=padding_mode,
+                      align_corners=align_corners, deterministic=deterministic) if len(frames0) else []
+    seg = label_warp_blend([labels0, labels1], num_classes, [for_flow, back_flow], blends=[for_mask, back_mask],
+                           signs=[-1.0, +1.0], padding_mode=padding_mode, align_corners=align_corners)
+    return [*outs, seg]

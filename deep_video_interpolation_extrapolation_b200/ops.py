@@ -318,6 +318,167 @@ def flow_warp_blend(
     return outs
 
 
+def _fill_dirs(p, flows, gates, blends, signs):
+    for d, f in enumerate(flows):
+        D = p.dir[d]
+        D.flow = f.data_ptr()
+        D.flow_sn, D.flow_sc, D.flow_st, D.flow_sh = f.stride()[:4]
+        if gates[d] is not None:
+            D.gate = gates[d].data_ptr()
+            D.gate_sn, D.gate_st, D.gate_sh = gates[d].stride()[:3]
+        if blends[d] is not None:
+            D.blend = blends[d].data_ptr()
+            D.blend_sn, D.blend_st, D.blend_sh = blends[d].stride()[:3]
+        D.sign = float(signs[d])
+
+
+class _LabelWarpFn(torch.autograd.Function):
+    """tensors = flows[D] + gates[D] + blends[D] (canonical 5-D / 4-D); labels[D] uint8 [N,T,H,W] ride in cfg-side args."""
+
+    @staticmethod
+    def forward(ctx, cfg: _Cfg, K: int, labels, *tensors):
+        D = cfg.n_dirs
+        tensors = tuple(_wcontig(t) for t in tensors)
+        flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        dev = flows[0].device
+        out = torch.empty((cfg.N, cfg.T, K, cfg.H, cfg.W), dtype=torch.float32, device=dev)
+        lib = L.load()
+        with torch.cuda.device(dev):
+            p = _LabelWarpFn._problem(cfg, K, labels, flows, gates, blends)
+            p.out = out.data_ptr()
+            p.out_sn, p.out_st, p.out_sc, p.out_sh = out.stride()[:4]
+            L.check(lib.fwb_label_warp_blend_forward(ctypes.byref(p), _stream_ptr(dev)), "fwb_label_warp_blend_forward")
+        ctx.cfg, ctx.K, ctx.labels = cfg, K, labels
+        ctx.save_for_backward(*[t for t in tensors if t is not None])
+        ctx.present = [t is not None for t in tensors]
+        return out
+
+    @staticmethod
+    def _problem(cfg, K, labels, flows, gates, blends):
+        p = L.fwb_label_problem()
+        p.N, p.T, p.H, p.W, p.n_dirs, p.K = cfg.N, cfg.T, cfg.H, cfg.W, cfg.n_dirs, K
+        p.padding_mode, p.align_corners = cfg.padding_mode, int(cfg.align_corners)
+        _fill_dirs(p, flows, gates, blends, cfg.signs)
+        for d, lab in enumerate(labels):
+            p.labels[d] = lab.data_ptr()
+            p.lab_sn[d], p.lab_st[d], p.lab_sh[d] = lab.stride()[:3]
+        return p
+
+    @staticmethod
+    def backward(ctx, go):
+        cfg: _Cfg = ctx.cfg
+        D = cfg.n_dirs
+        it = iter(ctx.saved_tensors)
+        tensors = [next(it) if pr else None for pr in ctx.present]
+        flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        need = ctx.needs_input_grad[3:]
+        dev = flows[0].device
+        N, T, H, W = cfg.N, cfg.T, cfg.H, cfg.W
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_flows = [torch.empty((N, 2, T, H, W), **f32) if need[d] else None for d in range(D)]
+        g_gates = [torch.empty((N, T, H, W), **f32) if (need[D + d] and gates[d] is not None) else None for d in range(D)]
+        g_blends = [torch.empty((N, T, H, W), **f32) if (need[2 * D + d] and blends[d] is not None) else None for d in range(D)]
+        if any(x is not None for x in g_flows + g_gates + g_blends):
+            go = _wcontig(go)
+            lib = L.load()
+            with torch.cuda.device(dev):
+                p = _LabelWarpFn._problem(cfg, ctx.K, ctx.labels, flows, gates, blends)
+                p.grad_out = go.data_ptr()
+                p.go_sn, p.go_st, p.go_sc, p.go_sh = go.stride()[:4]
+                for d in range(D):
+                    if g_flows[d] is not None:
+                        p.grad_flow[d] = g_flows[d].data_ptr()
+                        p.gf_sn[d], p.gf_sc[d], p.gf_st[d], p.gf_sh[d] = g_flows[d].stride()[:4]
+                    if g_gates[d] is not None:
+                        p.grad_gate[d] = g_gates[d].data_ptr()
+                        p.gg_sn[d], p.gg_st[d], p.gg_sh[d] = g_gates[d].stride()[:3]
+                    if g_blends[d] is not None:
+                        p.grad_blend[d] = g_blends[d].data_ptr()
+                        p.gb_sn[d], p.gb_st[d], p.gb_sh[d] = g_blends[d].stride()[:3]
+                p.accumulate = 0
+                L.check(lib.fwb_label_warp_blend_backward(ctypes.byref(p), _stream_ptr(dev)), "fwb_label_warp_blend_backward")
+        return (None, None, None, *g_flows, *g_gates, *g_blends)
+
+
+def label_warp_blend(
+    labels: Union[Tensor, Sequence[Tensor]], num_classes: int, flows: Union[Tensor, Sequence[Tensor]],
+    gates: Union[None, Tensor, Sequence[Optional[Tensor]]] = None,
+    blends: Union[None, Tensor, Sequence[Optional[Tensor]]] = None,
+    signs: Union[None, float, Sequence[float]] = None, padding_mode: str = "zeros", align_corners: bool = False,
+) -> Tensor:
+    """flow_warp_blend for a segmentation map given as uint8 LABELS: returns what
+    `flow_warp_blend([one_hot(labels_d) for d], flows, ...)` returns ([N,K,H,W] or [N,T,K,H,W], float32), bit for bit,
+    reading 1 byte per tap instead of 4*K (the reference one-hots in folder.py:193-200 and warps the
+    K float planes, nets/VAE_S.py:135).  labels: one uint8 tensor per direction, [N,H,W] / [N,1,H,W] / [N,T,H,W];
+    labels >= num_classes belong to no class.  Gradients flow to flows, gates and blends (labels have none).
+    """
+    if isinstance(flows, Tensor):
+        flows = [flows]
+    flows = list(flows)
+    D = len(flows)
+    if D not in (1, 2):
+        raise ValueError(f"label_warp_blend: 1 or 2 directions supported, got {D}")
+    labels = [labels] if isinstance(labels, Tensor) else list(labels)
+    if len(labels) != D:
+        raise ValueError(f"label_warp_blend: one label map per direction expected ({D}), got {len(labels)}")
+    if not 1 <= int(num_classes) <= 256:
+        raise ValueError("num_classes must be in 1..256")
+    gates, blends = _as_list(gates, D, "gates"), _as_list(blends, D, "blends")
+    if signs is None:
+        signs = [-1.0] * D
+    elif isinstance(signs, (int, float)):
+        signs = [float(signs)] * D
+    signs = tuple(float(s) for s in signs)
+    if len(signs) != D or any(s not in (-1.0, 1.0) for s in signs):
+        raise ValueError("signs: one of -1/+1 per direction")
+    if padding_mode not in ("zeros", "border"):
+        raise ValueError(f"padding_mode must be 'zeros' or 'border', got {padding_mode!r}")
+    f0 = flows[0]
+    for t in [x for x in flows + gates + blends if x is not None]:
+        if not t.is_cuda:
+            raise RuntimeError("label_warp_blend: CUDA tensors required (this library has no CPU path)")
+        if t.device != f0.device:
+            raise RuntimeError(f"label_warp_blend: all tensors must be on {f0.device}, got {t.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"label_warp_blend: float32 required, got {t.dtype}")
+    five_d = any(f.dim() == 5 for f in flows)
+    cflows = []
+    for f in flows:
+        if f.dim() == 4:
+            f = f.unsqueeze(2)
+        if f.dim() != 5 or f.shape[1] != 2:
+            raise RuntimeError(f"flow must be [N,2,H,W] or [N,2,T,H,W], got {tuple(f.shape)}")
+        cflows.append(f)
+    N, _, T, H, W = cflows[0].shape
+    if H < 1 or W < 1:
+        raise RuntimeError(f"label_warp_blend: non-empty spatial dims required, got H={H} W={W}")
+    for f in cflows:
+        if tuple(f.shape) != (N, 2, T, H, W):
+            raise RuntimeError("label_warp_blend: all flows must share one shape")
+    clabels = []
+    for lab in labels:
+        if not lab.is_cuda or lab.device != f0.device:
+            raise RuntimeError("label_warp_blend: labels must be CUDA tensors on the flows' device")
+        if lab.dtype != torch.uint8:
+            raise RuntimeError(f"label_warp_blend: uint8 labels required, got {lab.dtype}")
+        if lab.dim() == 3:
+            lab = lab.unsqueeze(1)
+        if lab.dim() != 4 or lab.shape[0] != N or lab.shape[1] not in (1, T) or tuple(lab.shape[2:]) != (H, W):
+            raise RuntimeError(f"labels must be [N,H,W], [N,1,H,W] or [N,T,H,W], got {tuple(lab.shape)}")
+        if lab.stride(-1) != 1 and W > 1:
+            lab = lab.contiguous()
+        clabels.append(lab.expand(N, T, H, W) if lab.shape[1] != T else lab)
+    cgates = [_canon_mask(m, N, T, H, W, "gate") for m in gates]
+    cblends = [_canon_mask(m, N, T, H, W, "blend") for m in blends]
+    if N == 0:
+        out = f0.new_empty((0, T, int(num_classes), H, W))
+        return out if five_d else out.squeeze(1)
+    cfg = _Cfg(D, 1, signs, L.FWB_PAD_BORDER if padding_mode == "border" else L.FWB_PAD_ZEROS, bool(align_corners), True,
+               N, T, H, W)
+    out = _LabelWarpFn.apply(cfg, int(num_classes), tuple(clabels), *cflows, *cgates, *cblends)
+    return out if five_d else out.squeeze(1)
+
+
 def _fill_blend(inp: Tensor, mask: Tensor, noise: Optional[Tensor]) -> "L.fwb_blend":
     b = L.fwb_blend()
     N, T, C, H, W = inp.shape

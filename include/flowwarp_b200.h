@@ -146,6 +146,35 @@ typedef struct fwb_blend {
   int64_t gn_sn, gn_sc, gn_sh;
 } fwb_blend;
 
+/* Compact segmentation format: the K-class map is given as uint8 LABELS [N,T,H,W] instead of the
+ * K-channel one-hot float tensor the reference's loader builds (folder.py:193-200) and warps with the RGB frame's flow
+ * (nets/VAE_S.py:134-135, nets/InterNet.py:15-18).  out[N,T,K,H,W] is bit-identical to the dense op applied to
+ * one_hot(labels); labels >= K belong to no class.  There is no gradient w.r.t. the labels; the backward produces the
+ * label warp's contribution to grad_flow / grad_gate / grad_blend, overwriting them (accumulate = 0) or adding to what
+ * the RGB backward already wrote there (accumulate = 1, same stream).  `dir` as in fwb_problem. */
+typedef struct fwb_label_problem {
+  int32_t N, T, H, W;
+  int32_t n_dirs; /* 1 or 2 */
+  int32_t K;      /* classes = output channels, 1..256 */
+  int32_t padding_mode;
+  int32_t align_corners;
+  fwb_dir dir[2];
+  const uint8_t* labels[2]; /* per direction, [N,T,H,W] uint8 (T-stride 0 when one map feeds all T) */
+  int64_t lab_sn[2], lab_st[2], lab_sh[2];
+  float* out; /* [N,T,K,H,W] (forward) */
+  int64_t out_sn, out_st, out_sc, out_sh;
+  const float* grad_out; /* [N,T,K,H,W] (backward) */
+  int64_t go_sn, go_st, go_sc, go_sh;
+  float* grad_flow[2]; /* [N,2,T,H,W] or NULL */
+  int64_t gf_sn[2], gf_sc[2], gf_st[2], gf_sh[2];
+  float* grad_gate[2]; /* [N,T,H,W] or NULL */
+  int64_t gg_sn[2], gg_st[2], gg_sh[2];
+  float* grad_blend[2]; /* [N,T,H,W] or NULL */
+  int64_t gb_sn[2], gb_st[2], gb_sh[2];
+  int32_t accumulate;
+  int32_t _pad;
+} fwb_label_problem;
+
 /* Library version (FWB_VERSION of the build). */
 int32_t fwb_version(void);
 
@@ -167,6 +196,10 @@ int32_t fwb_warp_blend_forward_zero(const fwb_problem* p, const fwb_grads* g, vo
 /* `refine`'s mask blend (utils/net_utils.py:141-143), see fwb_blend above. */
 int32_t fwb_mask_blend_forward(const fwb_blend* b, void* stream);
 int32_t fwb_mask_blend_backward(const fwb_blend* b, void* stream);
+
+/* Label-map warp (+ gate) (+ blend), see fwb_label_problem above. */
+int32_t fwb_label_warp_blend_forward(const fwb_label_problem* p, void* stream);
+int32_t fwb_label_warp_blend_backward(const fwb_label_problem* p, void* stream);
 
 /* Debug / parity: integer sample indices and validity bits of direction `d`.
  * x0,y0: int32 [N,T,H,W] contiguous; valid: uint8 [N,T,H,W], bit0 nw, bit1 ne, bit2 sw, bit3 se.

@@ -621,3 +621,77 @@ def test_mask_blend_vs_reference_refine_golden(pkg, golden_dir, name):
     assert relerr(ti.grad, z["grad_input"]) <= BWD_TOL
     assert relerr(tm.grad, z["grad_mask"]) <= BWD_TOL
     assert relerr(tn.grad, z["grad_noise"]) <= BWD_TOL
+
+
+# ---------------------------------------------------------------- compact segmentation format: uint8 labels
+def _labels(seed, N, H, W, K=20, T=None):
+    rng = np.random.default_rng(seed)
+    shape = (N, (H + 7) // 8, (W + 7) // 8) if T is None else (N, T, (H + 7) // 8, (W + 7) // 8)
+    lab = rng.integers(0, K, shape).astype(np.uint8)
+    return np.ascontiguousarray(lab.repeat(8, -2).repeat(8, -1)[..., :H, :W])  # blocky map, like synth.seg
+
+
+@pytest.mark.parametrize("pad,align", [("border", False), ("zeros", False), ("zeros", True)])
+@pytest.mark.parametrize("shape", [(2, 48, 80), (1, 37, 53)])
+def test_label_warp_blend_equals_dense_on_one_hot(pkg, oracle, shape, pad, align):
+    """label_warp_blend(labels) is bit-identical to the dense op on one_hot(labels) (which is pinned to the reference), and
+    its flow / mask gradients agree with the dense op's and with the fp64 oracle at the backward bar."""
+    N, H, W = shape
+    K = 20
+    l0, l1 = _labels(21, N, H, W, K), _labels(22, N, H, W, K)
+    l0[0, :3, :5] = 200  # labels >= K belong to no class
+    ff, fb = synth.flow(3, N, H, W, 8.0, oob_frac=0.05), synth.flow(4, N, H, W, 8.0, oob_frac=0.05)
+    mf, mb = synth.mask(2, N, H, W), synth.mask(12, N, H, W)
+    go = synth.grad(5, (N, K, H, W))
+    oh = lambda l: (np.arange(K)[None, :, None, None] == l[:, None]).astype(np.float32)  # noqa: E731
+    A = [cu(a, True) for a in (ff, fb, mf, mb)]
+    B = [cu(a, True) for a in (ff, fb, mf, mb)]
+    out = pkg.label_warp_blend([cu(l0), cu(l1)], K, A[:2], blends=A[2:], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    dense = pkg.flow_warp_blend([(cu(oh(l0)), cu(oh(l1)))], B[:2], blends=B[2:], signs=[-1, 1], padding_mode=pad, align_corners=align)[0]
+    assert torch.equal(out, dense)
+    ref = oracle.forward([(oh(l0), oh(l1))], [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)[0][:, 0]
+    assert relerr(out, ref) <= FWD_TOL
+    out.backward(cu(go))
+    dense.backward(cu(go))
+    rg = oracle.backward([(oh(l0), oh(l1))], [ff, fb], [go], blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    refs = [rg["grad_flows"][0][:, :, 0], rg["grad_flows"][1][:, :, 0], rg["grad_blends"][0], rg["grad_blends"][1]]
+    for a, b, r in zip(A, B, refs):
+        assert relerr(a.grad, b.grad) <= BWD_TOL
+        assert relerr(a.grad, r) <= BWD_TOL
+
+
+def test_label_warp_T_frames_gated_and_composite(pkg, oracle):
+    """`warp`-style use: one label map, T gated flows (T-stride 0 labels), one direction; and warp_blend_labels = RGB through
+    the dense kernels + seg through the label kernels with summed flow / mask gradients."""
+    N, T, H, W, K = 2, 3, 40, 64, 20
+    lab = _labels(31, N, H, W, K)
+    fl, gate = synth.flow(41, N, H, W, 4.0, T=T, oob_frac=0.05), synth.mask(42, N, H, W, T=T)
+    oh = (np.arange(K)[None, :, None, None] == lab[:, None]).astype(np.float32)
+    tf, tg = cu(fl, True), cu(gate, True)
+    out = pkg.label_warp_blend(cu(lab), K, tf, gates=tg, signs=-1.0)
+    ref = oracle.forward([oh], [fl], gates=[gate])[0]
+    assert tuple(out.shape) == (N, T, K, H, W) and relerr(out, ref) <= FWD_TOL
+    go = synth.grad(43, (N, T, K, H, W))
+    out.backward(cu(go))
+    rg = oracle.backward([oh], [fl], [go], gates=[gate])
+    assert relerr(tf.grad, rg["grad_flows"][0]) <= BWD_TOL
+    assert relerr(tg.grad, rg["grad_gates"][0]) <= BWD_TOL
+    # composite
+    N, H, W = 2, 48, 64
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    l0, l1 = _labels(51, N, H, W, K), _labels(52, N, H, W, K)
+    oh = lambda l: (np.arange(K)[None, :, None, None] == l[:, None]).astype(np.float32)  # noqa: E731
+    A = [cu(a, True) for a in (f0[0], f1[0], ff, fb, mf, mb)]
+    B = [cu(a, True) for a in (f0[0], f1[0], ff, fb, mf, mb)]
+    oa = pkg.warp_blend_labels([A[0]], [A[1]], cu(l0), cu(l1), K, A[2], A[3], A[4], A[5])
+    ob = pkg.warp_blend([B[0], cu(oh(l0))], [B[1], cu(oh(l1))], B[2], B[3], B[4], B[5])
+    for x, y in zip(oa, ob):
+        assert torch.equal(x, y)
+    torch.autograd.backward(oa, [cu(g) for g in gos])
+    torch.autograd.backward(ob, [cu(g) for g in gos])
+    for a, b in zip(A, B):
+        assert relerr(a.grad, b.grad) <= BWD_TOL
+    with pytest.raises(RuntimeError):
+        pkg.label_warp_blend(cu(l0).float(), K, A[2])
+    with pytest.raises(RuntimeError):
+        pkg.label_warp_blend(cu(l0).cpu(), K, A[2])

@@ -38,6 +38,8 @@ def test_struct_layout_matches_c_compiler():
 #include "flowwarp_b200.h"
 int main(void){
   printf("%zu %zu %zu %zu ", sizeof(fwb_dir), sizeof(fwb_group), sizeof(fwb_problem), sizeof(fwb_grads));
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(fwb_blend), sizeof(fwb_label_problem), offsetof(fwb_blend, grad_noise),
+         offsetof(fwb_blend, out), offsetof(fwb_label_problem, labels), offsetof(fwb_label_problem, accumulate));
   printf("%zu %zu %zu %zu %zu %zu\n", offsetof(fwb_dir, sign), offsetof(fwb_group, out), offsetof(fwb_problem, dir),
          offsetof(fwb_problem, grp), offsetof(fwb_grads, grad_src), offsetof(fwb_grads, grad_blend));
   return 0; }'''
@@ -47,6 +49,8 @@ int main(void){
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "a")], check=True)
         got = [int(v) for v in subprocess.run([os.path.join(d, "a")], capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(L.fwb_dir), ctypes.sizeof(L.fwb_group), ctypes.sizeof(L.fwb_problem), ctypes.sizeof(L.fwb_grads),
+            ctypes.sizeof(L.fwb_blend), ctypes.sizeof(L.fwb_label_problem), L.fwb_blend.grad_noise.offset, L.fwb_blend.out.offset,
+            L.fwb_label_problem.labels.offset, L.fwb_label_problem.accumulate.offset,
             L.fwb_dir.sign.offset, L.fwb_group.out.offset, L.fwb_problem.dir.offset, L.fwb_problem.grp.offset,
             L.fwb_grads.grad_src.offset, L.fwb_grads.grad_blend.offset]
     assert got == want
