@@ -168,6 +168,26 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     cx.irow[q] = i0 + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
     cx.inimg[q] = cx.j < G.W && cx.irow[q] < G.H;
   }
+  // all global loads of the prologue first (flow x/y, gate, blend weight of every (pixel, direction)): ONE exposed
+  // memory latency instead of one per (q, d) (the votes / atomics below keep the compiler from hoisting them itself).
+  // Out-of-image pixels of ragged tiles read the clamped in-image address and are masked afterwards.
+  float lfx[PPT][NDIRS], lfy[PPT][NDIRS], lgt[PPT][NDIRS], lbl[PPT][NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const DirP& D = P.dir[d];
+    const DirAt at = dir_at(D, cx.n, cx.t);
+    const int fsh = (int)D.flow_sh, gsh = (int)D.gate_sh, bsh = (int)D.blend_sh;
+    const int jc = min(cx.j, G.W - 1);
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int ic = min(cx.irow[q], G.H - 1);
+      const int of = ic * fsh + jc;
+      lfx[q][d] = __ldg(at.flow + of);
+      lfy[q][d] = __ldg(at.flow + D.flow_sc + of);
+      lgt[q][d] = at.gate ? __ldg(at.gate + (ic * gsh + jc)) : 1.0f;
+      lbl[q][d] = at.blend ? __ldg(at.blend + (ic * bsh + jc)) : 1.0f;
+    }
+  }
   int x0[PPT][NDIRS], y0[PPT][NDIRS];
   unsigned vld[PPT][NDIRS];
   if (threadIdx.x < NDIRS * TL_ROWS_P) {
@@ -187,9 +207,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
     const DirP& D = P.dir[d];
-    const DirAt at = dir_at(D, cx.n, cx.t);
-    const float* fyp = at.flow + D.flow_sc;
-    const int fsh = (int)D.flow_sh, gsh = (int)D.gate_sh, bsh = (int)D.blend_sh;
+    const bool gated = D.gate != nullptr;
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       TilePix& px = cx.px[q][d];
@@ -198,15 +216,12 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
       x0[q][d] = y0[q][d] = 0;
       vld[q][d] = 0u;
       if (cx.inimg[q]) {
-        const int i = cx.irow[q];
-        const int of = i * fsh + cx.j;
-        float fx = __ldg(at.flow + of), fy = __ldg(fyp + of);
-        if (at.gate) {
-          const float gate = __ldg(at.gate + (i * gsh + cx.j));
-          fx = __fmul_rn(fx, gate);
-          fy = __fmul_rn(fy, gate);
+        float fx = lfx[q][d], fy = lfy[q][d];
+        if (gated) {
+          fx = __fmul_rn(fx, lgt[q][d]);
+          fy = __fmul_rn(fy, lgt[q][d]);
         }
-        px.bl = at.blend ? __ldg(at.blend + (i * bsh + cx.j)) : 1.0f;
+        px.bl = lbl[q][d];
         // bx -/+ f as one fma: sign * f is exact, so this is the same single rounding as __fsub_rn / __fadd_rn
         const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by[q]);
         const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1);
@@ -580,6 +595,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   __shared__ __align__(16) TileChanB tab[TL_MAXCH];
   __shared__ unsigned amax_s[3];
   __shared__ int nchan_s, g0_s;
+  __shared__ float slowacc[TL_MAXSLOW][NDIRS][3];  // gix, giy, grad_blend of the slow pixels, summed over the channels
   const Geo& G = P.geo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int n, t, j, total, stage_f;
@@ -649,6 +665,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
     }
   }
   if (threadIdx.x < 3) amax_s[threadIdx.x] = 0u;
+  if (threadIdx.x < TL_MAXSLOW * NDIRS * 3) (&slowacc[0][0][0])[threadIdx.x] = 0.f;
   if (threadIdx.x >= 32 && threadIdx.x < 32 + slow.n) {  // the slow path of the backward needs the full taps (multipliers, raw flow)
     const int sidx = threadIdx.x - 32, pix = slow.pix[sidx];
 #pragma unroll
@@ -745,17 +762,40 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   float go[PPT], gn[PPT];
   load_go(0, go);
   vote_amax(go, 0);
-  // slow pixels, while the first copies are in flight: one warp per pixel, lanes over the channels
-  for (int s = warp; s < slow.n; s += TL_THREADS / 32) {
-    const int pix = slow.pix[s];
-    const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
-    bwdflow_slow_warp<NDIRS>(P, Q, n, t, si, sj, slowtap[s]);
-    for (int cf = lane; cf < Cn; cf += 32) {
+  // slow pixels, while the first copies are in flight: one (pixel, channel) item per thread, all loads of an item
+  // independent (one exposed memory latency, the eight warps evenly loaded); the coordinate-gradient partial sums over
+  // the channels meet in shared memory and are stored after the channel loop
+  {
+    const int nslow = slow.n;
+    const int sh0 = P.grp[g0].src_sh[0], sh1 = P.grp[g0].src_sh[NDIRS - 1];
+    for (int it = threadIdx.x; it < nslow * Cn; it += TL_THREADS) {
+      const int cf = it / nslow, sidx = it - cf * nslow, pix = slow.pix[sidx];  // lanes = different pixels: no same-address
+      const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
       const TileChanB& tc = tab[cf];
       const float gout = __ldg(tc.go + si * Q.go_sh[g0] + sj);
+      float va[NDIRS][4];
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d)
-        scatter_atomic_px(Q, tc.g, d, n, t, tc.c, false, slowtap[s][d], has_bl[d] ? gout * slowtap[s][d].blend : gout, 0.f);
+      for (int d = 0; d < NDIRS; ++d) {
+        const Tap& k = slowtap[sidx][d];
+        const int sh = d == 0 ? sh0 : sh1;
+        const float* sp = tc.src[d] + k.y0 * sh + k.x0;
+        va[d][0] = ldg_if(sp, k.valid & 1u), va[d][1] = ldg_if(sp + 1, k.valid & 2u);
+        va[d][2] = ldg_if(sp + sh, k.valid & 4u), va[d][3] = ldg_if(sp + sh + 1, k.valid & 8u);
+      }
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const Tap& k = slowtap[sidx][d];
+        const float a = va[d][0], b = va[d][1], cc = va[d][2], dd = va[d][3];
+        float gw = gout;
+        if (has_bl[d]) {
+          const float top = fmaf(b, k.tx, a * k.ux), bot = fmaf(dd, k.tx, cc * k.ux);
+          atomicAdd(&slowacc[sidx][d][2], gout * fmaf(bot, k.ty, top * k.uy));
+          gw = gout * k.blend;
+        }
+        atomicAdd(&slowacc[sidx][d][0], gw * fmaf(k.ty, dd - cc, k.uy * (b - a)));
+        atomicAdd(&slowacc[sidx][d][1], gw * fmaf(k.tx, dd - b, k.ux * (cc - a)));
+        scatter_atomic_px(Q, tc.g, d, n, t, tc.c, false, k, gw, 0.f);
+      }
     }
   }
   constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: fma(x, y, MAGIC) holds round-to-nearest(x*y) in its low mantissa bits
@@ -827,6 +867,11 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   }
   __syncthreads();
   if (flush_prev) flush(Cn - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
+  if (threadIdx.x < slow.n * NDIRS) {  // coordinate gradients of the slow pixels
+    const int sidx = threadIdx.x / NDIRS, d = threadIdx.x - sidx * NDIRS, pix = slow.pix[sidx];
+    bwdflow_store(P, Q, d, n, t, blockIdx.y * (8 * PPT) + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d],
+                  slowacc[sidx][d][0], slowacc[sidx][d][1], slowacc[sidx][d][2]);
+  }
 
   // epilogue: coordinate gradient -> grad_flow / grad_gate / grad_blend.  The multipliers are d(ix)/d(gx) = W/2 or (W-1)/2,
   // zero where border padding clipped the coordinate; the raw flow and the gate are reloaded only when there is a gate.
