@@ -606,6 +606,22 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   unsigned info[SLOTS];
   unsigned pd[SLOTS];  // byte offset inside a stage of piece tid + s*256
   unsigned clipbits = 0u;  // 2 bits per (q, d): the coordinate gradient is zero (border clipping)
+  // grad_out of the first channel: issued before the prologue so that its latency hides behind it (the scale vote of
+  // channel 0 is the first thing the pipeline needs)
+  float ego[PPT];
+  {
+    int g0e = 0;
+    while (g0e < G.n_groups - 1 && !Q.grad_out[g0e]) ++g0e;
+    const int nt = blockIdx.z, ne = G.T == 1 ? nt : nt / G.T, te = nt - ne * G.T;
+    const int je = blockIdx.x * TL_TW + (warp & 3) * 8 + (lane & 7);
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int ie = blockIdx.y * (8 * PPT) + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
+      ego[q] = (Q.grad_out[g0e] && je < G.W && ie < G.H)
+                   ? __ldcs(Q.grad_out[g0e] + ne * Q.go_sn[g0e] + te * Q.go_st[g0e] + (long long)ie * Q.go_sh[g0e] + je)
+                   : 0.f;
+    }
+  }
   {
     TileCtx<NDIRS, PPT, SLOTS> cx;
     tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
@@ -666,11 +682,6 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   }
   if (threadIdx.x < 3) amax_s[threadIdx.x] = 0u;
   if (threadIdx.x < TL_MAXSLOW * NDIRS * 3) (&slowacc[0][0][0])[threadIdx.x] = 0.f;
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + slow.n) {  // the slow path of the backward needs the full taps (multipliers, raw flow)
-    const int sidx = threadIdx.x - 32, pix = slow.pix[sidx];
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) compute_tap(G, P.dir[d], n, t, blockIdx.y * (8 * PPT) + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d]);
-  }
   bool has_bl[NDIRS];
   float blmax[PPT];
 #pragma unroll
@@ -760,7 +771,8 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
     for (int p = 0; p < TL_BD - 1; ++p, so += stage_b) issue(p, so);
   }
   float go[PPT], gn[PPT];
-  load_go(0, go);
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) go[q] = (Cn > 0 && act[q]) ? ego[q] : 0.f;  // channel 0 (loaded before the prologue)
   vote_amax(go, 0);
   // slow pixels, while the first copies are in flight: one (pixel, channel) item per thread, all loads of an item
   // independent (one exposed memory latency, the eight warps evenly loaded); the coordinate-gradient partial sums over
@@ -869,8 +881,10 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   if (flush_prev) flush(Cn - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
   if (threadIdx.x < slow.n * NDIRS) {  // coordinate gradients of the slow pixels
     const int sidx = threadIdx.x / NDIRS, d = threadIdx.x - sidx * NDIRS, pix = slow.pix[sidx];
-    bwdflow_store(P, Q, d, n, t, blockIdx.y * (8 * PPT) + (pix >> 5), blockIdx.x * TL_TW + (pix & 31), slowtap[sidx][d],
-                  slowacc[sidx][d][0], slowacc[sidx][d][1], slowacc[sidx][d][2]);
+    const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
+    Tap k;  // the full tap (gradient multipliers, raw flow, gate): only needed here
+    compute_tap(G, P.dir[d], n, t, si, sj, k);
+    bwdflow_store(P, Q, d, n, t, si, sj, k, slowacc[sidx][d][0], slowacc[sidx][d][1], slowacc[sidx][d][2]);
   }
 
   // epilogue: coordinate gradient -> grad_flow / grad_gate / grad_blend.  The multipliers are d(ix)/d(gx) = W/2 or (W-1)/2,
