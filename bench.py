@@ -492,7 +492,7 @@ def main():
     ap.add_argument("--zero", default="fwd", choices=["fwd", "memset", "side"],
                     help="who zero-fills grad_src before the fused backward: the forward kernel (default), the backward's "
                          "memsets, or a side stream (A/B)")
-    ap.add_argument("--e2e-chunk", type=int, default=1, help="clips per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="clips per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--aux", action="store_true", help="also time the mask-blend (refine) kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")

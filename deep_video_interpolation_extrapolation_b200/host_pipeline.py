@@ -96,7 +96,7 @@ class HostWarpBlend:
 
     SLOTS = 3
 
-    def __init__(self, device, chunk: int = 1, padding_mode: str = "border", align_corners: bool = False,
+    def __init__(self, device, chunk: int = 2, padding_mode: str = "border", align_corners: bool = False,
                  deterministic: bool = False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -205,7 +205,7 @@ class HostWarpBlend:
                 res["grad_for_mask"], res["grad_back_mask"]]
 
 
-def warp_blend_host(frames0, frames1, for_flow, back_flow, for_mask, back_mask, grad_outs, device="cuda:0", chunk: int = 1,
+def warp_blend_host(frames0, frames1, for_flow, back_flow, for_mask, back_mask, grad_outs, device="cuda:0", chunk: int = 2,
                     **kw):
     """One-shot form of `HostWarpBlend(device, chunk, **kw).run(...)`."""
     return HostWarpBlend(device, chunk, **kw).run(frames0, frames1, for_flow, back_flow, for_mask, back_mask, grad_outs)
