@@ -14,8 +14,9 @@ from typing import Callable, Optional, Sequence
 from . import _lib as L
 
 
-def _chk_w(st, what):
-    if st[-1] != 1:
+def _chk_w(st, what, W=None):
+    # a size-1 innermost dimension may carry any stride (numpy / torch views do): it is never stepped over
+    if st[-1] != 1 and W != 1:
         raise ValueError(f"{what}: innermost (W) stride must be 1, got {st[-1]}")
 
 
@@ -34,17 +35,17 @@ def fill_problem(
     for d in range(p.n_dirs):
         D = p.dir[d]
         st = strides(flows[d])
-        _chk_w(st, "flow")
+        _chk_w(st, "flow", p.W)
         D.flow = ptr(flows[d])
         D.flow_sn, D.flow_sc, D.flow_st, D.flow_sh = st[0], st[1], st[2], st[3]
         if gates[d] is not None:
             st = strides(gates[d])
-            _chk_w(st, "gate")
+            _chk_w(st, "gate", p.W)
             D.gate = ptr(gates[d])
             D.gate_sn, D.gate_st, D.gate_sh = st[0], st[1], st[2]
         if blends[d] is not None:
             st = strides(blends[d])
-            _chk_w(st, "blend")
+            _chk_w(st, "blend", p.W)
             D.blend = ptr(blends[d])
             D.blend_sn, D.blend_st, D.blend_sh = st[0], st[1], st[2]
         D.sign = float(signs[d])
@@ -53,13 +54,13 @@ def fill_problem(
         for d in range(p.n_dirs):
             s = srcs[g][d]
             st = strides(s)
-            _chk_w(st, "src")
+            _chk_w(st, "src", p.W)
             R.src[d] = ptr(s)
             R.src_sn[d], R.src_st[d], R.src_sc[d], R.src_sh[d] = st[0], st[1], st[2], st[3]
         R.C = _shape(srcs[g][0])[2]
         if outs is not None and outs[g] is not None:
             st = strides(outs[g])
-            _chk_w(st, "out")
+            _chk_w(st, "out", p.W)
             R.out = ptr(outs[g])
             R.out_sn, R.out_st, R.out_sc, R.out_sh = st[0], st[1], st[2], st[3]
     return p
@@ -78,33 +79,33 @@ def fill_grads(
     for g in range(p.n_groups):
         if grad_outs[g] is not None:
             st = strides(grad_outs[g])
-            _chk_w(st, "grad_out")
+            _chk_w(st, "grad_out", p.W)
             q.grad_out[g] = ptr(grad_outs[g])
             q.go_sn[g], q.go_st[g], q.go_sc[g], q.go_sh[g] = st[0], st[1], st[2], st[3]
         for d in range(p.n_dirs):
             x = grad_srcs[g][d]
             if x is not None:
                 st = strides(x)
-                _chk_w(st, "grad_src")
+                _chk_w(st, "grad_src", p.W)
                 q.grad_src[g][d] = ptr(x)
                 q.gs_sn[g][d], q.gs_st[g][d], q.gs_sc[g][d], q.gs_sh[g][d] = st[0], st[1], st[2], st[3]
     for d in range(p.n_dirs):
         x = grad_flows[d]
         if x is not None:
             st = strides(x)
-            _chk_w(st, "grad_flow")
+            _chk_w(st, "grad_flow", p.W)
             q.grad_flow[d] = ptr(x)
             q.gf_sn[d], q.gf_sc[d], q.gf_st[d], q.gf_sh[d] = st[0], st[1], st[2], st[3]
         x = grad_gates[d]
         if x is not None:
             st = strides(x)
-            _chk_w(st, "grad_gate")
+            _chk_w(st, "grad_gate", p.W)
             q.grad_gate[d] = ptr(x)
             q.gg_sn[d], q.gg_st[d], q.gg_sh[d] = st[0], st[1], st[2]
         x = grad_blends[d]
         if x is not None:
             st = strides(x)
-            _chk_w(st, "grad_blend")
+            _chk_w(st, "grad_blend", p.W)
             q.grad_blend[d] = ptr(x)
             q.gb_sn[d], q.gb_st[d], q.gb_sh[d] = st[0], st[1], st[2]
     return q

@@ -23,6 +23,9 @@
 
 namespace fwb {
 
+#ifndef TL_FWD_MINCTA
+#define TL_FWD_MINCTA 3  // resident CTAs per SM the forward is compiled for (4 = 64 registers: spills, measured below)
+#endif
 constexpr int TL_TW = 32, TL_TH = 16;
 constexpr int TL_THREADS = 256;
 constexpr int TL_PPT = 2;       // pixels per thread
@@ -428,7 +431,7 @@ __device__ __forceinline__ void st_zero4_if(float* p, bool on) {
 }
 
 template <int NDIRS, bool ALIGN, bool BORDER>
-__global__ void __launch_bounds__(TL_THREADS, 3) fwd_tile_kernel(const __grid_constant__ Params P, int smem_floats, int Ctot,
+__global__ void __launch_bounds__(TL_THREADS, TL_FWD_MINCTA) fwd_tile_kernel(const __grid_constant__ Params P, int smem_floats, int Ctot,
                                                                  const __grid_constant__ ZeroP Z) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);

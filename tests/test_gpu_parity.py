@@ -695,3 +695,55 @@ def test_label_warp_T_frames_gated_and_composite(pkg, oracle):
         pkg.label_warp_blend(cu(l0).float(), K, A[2])
     with pytest.raises(RuntimeError):
         pkg.label_warp_blend(cu(l0).cpu(), K, A[2])
+
+
+# ---------------------------------------------------------------- seeded random sweep of the whole option space
+def _random_case(rng):
+    N, T = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+    H, W = int(rng.integers(1, 70)), int(rng.choice([1, 3, 4, 8, 20, 36, 52, 64, 100, 132]))
+    D = int(rng.integers(1, 3))
+    Cs = [int(c) for c in rng.integers(1, 7, int(rng.integers(1, 4)))]
+    return dict(N=N, T=T, H=H, W=W, D=D, Cs=Cs, sigma=float(rng.choice([0.5, 3.0, 8.0, 40.0])), pad=str(rng.choice(["zeros", "border"])),
+                align=bool(rng.integers(0, 2)), gate=bool(rng.integers(0, 2)), blend=bool(rng.integers(0, 2)),
+                shared=bool(rng.integers(0, 2)), det=bool(rng.integers(0, 2)), seed=int(rng.integers(0, 1 << 30)))
+
+
+@pytest.mark.parametrize("k", range(int(os.environ.get("FWB_SWEEP", "24"))))
+def test_random_option_sweep_vs_oracle(pkg, oracle, k):
+    """Random (seeded) shapes and options through flow_warp_blend, forward and every gradient against the oracle: 1-2
+    directions, 1-3 channel groups, T frames with shared or per-frame sources, gates / blends on or off, both padding and
+    align modes, deterministic or fused backward, widths that take the tile path (W % 4 == 0) and widths that cannot."""
+    c = _random_case(np.random.default_rng(1000 + k))
+    N, T, H, W, D = c["N"], c["T"], c["H"], c["W"], c["D"]
+    sd = c["seed"]
+    signs = [-1.0, 1.0][:D]
+    srcs = [[(synth.rgb(sd + 10 * g + d, N, H, W, C)[:, None] if c["shared"] else
+              np.stack([synth.rgb(sd + 10 * g + d + 100 * t, N, H, W, C) for t in range(T)], 1)) for d in range(D)]
+            for g, C in enumerate(c["Cs"])]
+    flows = [synth.flow(sd + 3 + d, N, H, W, c["sigma"], T=T, oob_frac=0.03) for d in range(D)]
+    gates = [synth.mask(sd + 5 + d, N, H, W, T=T) if c["gate"] else None for d in range(D)]
+    blends = [synth.mask(sd + 7 + d, N, H, W, T=T) if c["blend"] else None for d in range(D)]
+    gos = [synth.grad(sd + 20 + g, (N, T, C, H, W)) for g, C in enumerate(c["Cs"])]
+    osrc = [tuple(np.broadcast_to(s, (N, T) + s.shape[2:]) for s in row) for row in srcs]
+    ref = oracle.forward(osrc, flows, gates=gates, blends=blends, signs=signs, padding_mode=c["pad"], align_corners=c["align"])
+    rg = oracle.backward(osrc, flows, gos, gates=gates, blends=blends, signs=signs, padding_mode=c["pad"], align_corners=c["align"])
+    ts = [[cu(s, True) for s in row] for row in srcs]
+    tf = [cu(f, True) for f in flows]
+    tg = [cu(g, True) if g is not None else None for g in gates]
+    tb = [cu(b, True) if b is not None else None for b in blends]
+    outs = pkg.flow_warp_blend([tuple(r) for r in ts], tf, gates=tg, blends=tb, signs=signs, padding_mode=c["pad"],
+                               align_corners=c["align"], deterministic=c["det"])
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    for g in range(len(c["Cs"])):
+        assert relerr(outs[g], ref[g]) <= FWD_TOL, c
+        for d in range(D):
+            want = rg["grad_srcs"][g][d]
+            if c["shared"] and want.shape[1] != 1:  # the oracle saw T distinct frames (a W == 1 broadcast view gets copied):
+                want = want.sum(axis=1, keepdims=True)  # the shared source's gradient is their sum
+            assert relerr(ts[g][d].grad, want) <= BWD_TOL, c
+    for d in range(D):
+        assert relerr(tf[d].grad, rg["grad_flows"][d]) <= BWD_TOL, c
+        if c["gate"]:
+            assert relerr(tg[d].grad, rg["grad_gates"][d]) <= BWD_TOL, c
+        if c["blend"]:
+            assert relerr(tb[d].grad, rg["grad_blends"][d]) <= BWD_TOL, c
