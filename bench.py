@@ -210,6 +210,30 @@ def run_reference_arm(args, cfg, rank, world):
     }))
 
 
+def stock_torch_gpu_step(inp):
+    """The composition the reference runs on its GPU today, restated inline (nothing imported from oracle/): base grid
+    built on the CPU and sent to the device on every call (utils/net_utils.py:96-107), `grid = base -/+ flow` (:109-111),
+    one F.grid_sample per modality and direction (:113, nets/VAE_S.py:134-135), mask weighting and sum
+    (nets/OpticalUnet.py:141-146), autograd backward.  The GPU baseline SURVEY 8d asks to time next to ours."""
+    import torch
+    import torch.nn.functional as F
+    leaves = [t.detach().clone().requires_grad_() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]]]
+    f0, f1, (ff, fb, mf, mb) = leaves[:2], leaves[2:4], leaves[4:]
+    N, _, H, W = ff.shape
+    outs = []
+    for a, b in zip(f0, f1):
+        warped = []
+        for x, fl, sign in ((a, ff, -1.0), (b, fb, 1.0)):
+            base = torch.zeros(N, H, W, 2)
+            base[..., 0] = torch.ger(torch.ones(H), torch.linspace(-1, 1, W))
+            base[..., 1] = torch.ger(torch.linspace(-1, 1, H), torch.ones(W))
+            grid = base.to(x.device) + sign * fl.transpose(1, 2).transpose(2, 3)
+            warped.append(F.grid_sample(x, grid, padding_mode="border", align_corners=False))
+        outs.append(mf * warped[0] + mb * warped[1])
+    torch.autograd.backward(outs, inp["gos"])
+    return outs
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 class CabiStep:
     """The three C-ABI entry points on preallocated device buffers (what the autograd op calls)."""
@@ -412,6 +436,22 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
                                            "note": "seg as uint8 labels (SURVEY 8f row 4): same outputs as the dense op on one-hot "
                                                    "maps, no seg source gradient; NOT the headline metric"}}
 
+    # ---- aux: the stock torch composition on this GPU, and other flow regimes, reported separately
+    regimes = None
+    if args.aux:
+        pixs = cfg["N"] * cfg["H"] * cfg["W"]
+        t_s = timed(lambda: stock_torch_gpu_step(inp), 5, 2, sync) / 5
+        regimes = {"gpu_stock_torch": {"ms_per_step": t_s * 1e3, "Gpix_per_s": pixs / t_s / 1e9,
+                                       "what": "reference composition on this GPU: CPU base grid + H2D per call, 4 x F.grid_sample, "
+                                               "mask weighting, autograd (torch " + torch.__version__ + ")"}}
+        for name, mk in (("sigma2_small", lambda f, k: f * (2.0 / cfg["sigma"])),
+                         ("adversarial_uniform_pm0.5", lambda f, k: (torch.rand(f.shape, generator=torch.Generator().manual_seed(k)) - 0.5).to(dev))):
+            alt = dict(inp, ff=mk(inp["ff"], 1).contiguous(), fb=mk(inp["fb"], 2).contiguous())
+            st2 = CabiStep(alt, args.deterministic, atomic_src=args.atomic_src, zero=args.zero)
+            t_r = timed(st2.step, 10, 3, sync) / 10
+            regimes[name] = {"ms_per_step": t_r * 1e3, "Gpix_per_s": pixs / t_r / 1e9, "frac_of_hbm_roofline": pixs * BYTES_PER_PIX / t_r / 1e9 / peaks()[0]}
+            del st2, alt
+
     # ---- e2e: public API for HOST buffers (HostWarpBlend: the autograd op per batch chunk, pinned host in -> pinned host
     # out, H2D of every input and D2H of every output / gradient inside the timed region, copies overlapped with compute)
     host_in = [t.cpu().pin_memory() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]] + inp["gos"]]
@@ -462,6 +502,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             out["aux_kernels"] = aux
         if variants:
             out["variants"] = variants
+        if regimes:
+            out["other_measurements"] = regimes
         if world == 1 and not args.no_cpu:
             v, cores, reps = time_cpu_reference(cfg, cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1, 10.0, 3, 30)
             ns = cfg["N"] if cfg["H"] * cfg["W"] <= 256 * 512 else 1
