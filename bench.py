@@ -423,13 +423,30 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             for t in lv:
                 t.grad = None
 
+        # flow-only backward: the sources are data (requires_grad=False), the usual training case; no grad_src traffic
+        fo = [t.detach() for t in inp["f0"] + inp["f1"]] + [t.detach().clone().requires_grad_() for t in (inp["ff"], inp["fb"], inp["mf"], inp["mb"])]
+
+        def flow_only_step():
+            outs = P.warp_blend(fo[0:2], fo[2:4], fo[4], fo[5], fo[6], fo[7])
+            torch.autograd.backward(outs, inp["gos"])
+            for t in fo[4:]:
+                t.grad = None
+
+        t_fo = timed(flow_only_step, 20, 3, sync) / 20
         t_l = timed(label_step, 20, 3, sync) / 20
         pix = cfg["N"] * cfg["H"] * cfg["W"]
         c3 = CH[0]
         # fwd: R 2 rgb frames 8*c3, 2 label maps 2, flows 16, masks 8, W out 4*(c3+K); bwd: R gout 4*(c3+K), rgb 8*c3, labels 2,
         # flows 16, masks 8, W grad rgb 8*c3, gflows 16, gmasks 8
         lb = (8 * c3 + 2 + 24 + 4 * (c3 + K)) + (4 * (c3 + K) + 8 * c3 + 2 + 24 + 8 * c3 + 24)
-        variants = {"compact_seg_labels": {"ms_per_step": t_l * 1e3, "Gpix_per_s": pix / t_l / 1e9, "bytes_per_pixel": lb,
+        fob = (12 * C_TOTAL + 24) + (12 * C_TOTAL + 48)  # fwd + (R gout 4C, R x0,x1 8C, flows 16, masks 8, W gflows 16, gmasks 8)
+        variants = {"no_source_gradient": {"ms_per_step": t_fo * 1e3, "Gpix_per_s": cfg["N"] * cfg["H"] * cfg["W"] / t_fo / 1e9,
+                                           "bytes_per_pixel": fob,
+                                           "frac": cfg["N"] * cfg["H"] * cfg["W"] * fob / t_fo / 1e9 / peaks()[0],
+                                           "api": "warp_blend + autograd.backward with requires_grad=False frames",
+                                           "note": "SURVEY 8a: reduced byte count when grad w.r.t. the sources is not needed; "
+                                                   "NOT the headline metric"},
+                    "compact_seg_labels": {"ms_per_step": t_l * 1e3, "Gpix_per_s": pix / t_l / 1e9, "bytes_per_pixel": lb,
                                            "GBps": pix * lb / t_l / 1e9, "frac": pix * lb / t_l / 1e9 / peaks()[0],
                                            "api": "warp_blend_labels + autograd.backward (RGB dense kernels + label kernels; "
                                                   "autograd sums the two flow / mask gradients)",

@@ -790,11 +790,14 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
             (Q.gs_sh[gi][d] & 3))
           ok = false;  // red.global.add.v4.f32 needs 16-byte aligned rows
       }
-    if (ok && any_src) {
+    // a backward without any grad_src (the sources are data: the usual training case) takes the tile kernel too: it then
+    // neither scatters nor flushes, i.e. it is kernel 2 on the staged tiles
+    const bool tile_ok = !(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g);
+    if (ok && (any_src || tile_ok)) {
       // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out) unless the
       // caller did (FWB_FLAG_GRAD_SRC_ZEROED, e.g. fwb_warp_blend_forward_zero)
-      if (!(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
-      if (!(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g)) {
+      if (any_src && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
+      if (tile_ok) {
         const int ppt = env_int("FWB_TILE_BWD_PPT", 2);  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
         const int sb = env_int("FWB_TILE_BWD_KB", ppt == 1 ? 48 : 80) * 1024;
         const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);
@@ -822,6 +825,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
 #undef FWB_LAUNCH_TBWD
         return (int32_t)cudaGetLastError();
       }
+      if (any_src) {
       const int sb = env_int("FWB_FUSED_KB", 100) * 1024;
 #define FWB_LAUNCH_FUSED(D, A, B)                                                        \
   do {                                                                                   \
@@ -841,6 +845,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
       }
 #undef FWB_LAUNCH_FUSED
       return (int32_t)cudaGetLastError();
+      }
     }
   }
   // the segment tables kernel 3 needs are produced whenever a workspace is supplied

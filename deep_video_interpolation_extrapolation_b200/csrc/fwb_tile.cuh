@@ -717,7 +717,8 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
     tsel[s] = 8u * (unsigned)d;
     const bool none = threadIdx.x + s * TL_THREADS >= total, zero = piece_zero(info[s]);
     poff[s] = none ? PIECE_NONE : zero ? PIECE_ZERO : piece_y(info[s]) * P.grp[g0].src_sh[d] + piece_col(info[s]);
-    goff[s] = (none || zero) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
+    // no group has a grad_src for this direction <=> group g0 has none (host-checked): nothing to flush
+    goff[s] = (none || zero || Q.grad_src[g0][d] == nullptr) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
   }
   int gooff[PPT];
 #pragma unroll

@@ -747,3 +747,29 @@ def test_random_option_sweep_vs_oracle(pkg, oracle, k):
             assert relerr(tg[d].grad, rg["grad_gates"][d]) <= BWD_TOL, c
         if c["blend"]:
             assert relerr(tb[d].grad, rg["grad_blends"][d]) <= BWD_TOL, c
+
+
+@pytest.mark.parametrize("which", ["none", "dir0_only", "rgb_only"])
+def test_backward_without_some_source_gradients(pkg, oracle, which):
+    """Sources that are data (requires_grad=False) get no grad_src buffer: the fused backward then runs the tile kernel
+    without scatter / flush for them.  Flow and mask gradients must not change; the requested source gradients neither."""
+    N, H, W = 2, 64, 96
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    need0 = {"none": [False, False], "dir0_only": [True, True], "rgb_only": [True, False]}[which]
+    need1 = {"none": [False, False], "dir0_only": [False, False], "rgb_only": [True, False]}[which]
+    t0 = [cu(a, n) for a, n in zip(f0, need0)]
+    t1 = [cu(a, n) for a, n in zip(f1, need1)]
+    tff, tfb, tmf, tmb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+    outs = pkg.warp_blend(t0, t1, tff, tfb, tmf, tmb)
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    assert relerr(tff.grad, rg["grad_flows"][0][:, :, 0]) <= BWD_TOL
+    assert relerr(tfb.grad, rg["grad_flows"][1][:, :, 0]) <= BWD_TOL
+    assert relerr(tmf.grad, rg["grad_blends"][0]) <= BWD_TOL
+    assert relerr(tmb.grad, rg["grad_blends"][1]) <= BWD_TOL
+    for g in range(2):
+        for d, (t, need) in enumerate(((t0[g], need0[g]), (t1[g], need1[g]))):
+            if need:
+                assert relerr(t.grad, rg["grad_srcs"][g][d][:, 0]) <= BWD_TOL
+            else:
+                assert t.grad is None
