@@ -510,7 +510,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "kernels": kernels,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "chunk": args.e2e_chunk,
-                    "api": "deep_video_interpolation_extrapolation_b200.HostWarpBlend.run (warp_blend + autograd.backward per batch chunk; "
+                    "api": "deep_video_interpolation_extrapolation_b200.HostWarpBlend.run (forward + backward C-ABI calls per batch chunk; "
                            "pinned host in/out, H2D | compute | D2H on three streams)"},
             "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
             "clocks": clocks,

@@ -158,7 +158,8 @@ __device__ __forceinline__ void tile_tab_scan(TileTab& tb, int slot_start4) {
 // overwrite later: the caller must __syncthreads() between this call and the first copy.
 // The slow pixels' taps are written to slowtap from the fast taps (enough for the forward).
 // Host-checked: the in-plane offsets of flow / gate / blend fit in 32 bits.
-template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS>
+// NTHR threads per CTA = NTHR/128 rows of four 8x4 warp patches per pixel slot: tile height 4 * (NTHR/128) * PPT
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS>
 __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, StageSlow& slow, Tap (*slowtap)[NDIRS],
                                               int budget_floats, int stages_needed, TileCtx<NDIRS, PPT, SLOTS>& cx) {
   const Geo& G = P.geo;
@@ -171,10 +172,11 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     cx.n = blockIdx.z / G.T;
     cx.t = blockIdx.z - cx.n * G.T;
   }
-  const int i0 = blockIdx.y * (8 * PPT);
+  constexpr int WY = NTHR / 128;
+  const int i0 = blockIdx.y * (4 * WY * PPT);
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
-    cx.irow[q] = i0 + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
+    cx.irow[q] = i0 + ((warp >> 2) + WY * q) * 4 + (lane >> 3);
     cx.inimg[q] = cx.j < G.W && cx.irow[q] < G.H;
   }
   // all global loads of the prologue first (flow x/y, gate, blend weight of every (pixel, direction)): ONE exposed
@@ -199,9 +201,9 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
   }
   int x0[PPT][NDIRS], y0[PPT][NDIRS];
   unsigned vld[PPT][NDIRS];
-  if (threadIdx.x < NDIRS * TL_ROWS_P) {
-    TileTab& T = tb[threadIdx.x >= TL_ROWS_P ? 1 : 0];
-    const int r = threadIdx.x >= TL_ROWS_P ? threadIdx.x - TL_ROWS_P : threadIdx.x;
+  for (int k = threadIdx.x; k < NDIRS * TL_ROWS_P; k += NTHR) {
+    TileTab& T = tb[k >= TL_ROWS_P ? 1 : 0];
+    const int r = k >= TL_ROWS_P ? k - TL_ROWS_P : k;
     T.xlo[r] = 0x7fffffff;
     T.xhi[r] = -0x7fffffff;
   }
@@ -319,7 +321,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
     alloc += tb[NDIRS - 1].alloc4;
   }
   cx.stage_f = TL_ZPAD + 4 * alloc;
-  if (cx.total > SLOTS * TL_THREADS || stages_needed * cx.stage_f > budget_floats) cx.ok = 0;
+  if (cx.total > SLOTS * NTHR || stages_needed * cx.stage_f > budget_floats) cx.ok = 0;
   if (!cx.ok) return;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
@@ -339,7 +341,7 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
   // which pieces this thread copies: piece k = tid + s*256 of the two directions' piece lists back to back
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    const int k = threadIdx.x + s * TL_THREADS;
+    const int k = threadIdx.x + s * NTHR;
     cx.info[s] = 0x8000u;
     cx.pdst[s] = 0;
     if (k < cx.total) {
@@ -594,8 +596,8 @@ __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, i
   scatter_atomic_px(Q, g, d, n, t, c, false, k, gw, 0.f);
 }
 
-template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS>
-__global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS>
+__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
                                                                  int smem_floats) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
     const int je = blockIdx.x * TL_TW + (warp & 3) * 8 + (lane & 7);
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
-      const int ie = blockIdx.y * (8 * PPT) + ((warp >> 2) + 2 * q) * 4 + (lane >> 3);
+      const int ie = blockIdx.y * (4 * (NTHR / 128) * PPT) + ((warp >> 2) + (NTHR / 128) * q) * 4 + (lane >> 3);
       ego[q] = (Q.grad_out[g0e] && je < G.W && ie < G.H)
                    ? __ldcs(Q.grad_out[g0e] + ne * Q.go_sn[g0e] + te * Q.go_st[g0e] + (long long)ie * Q.go_sh[g0e] + je)
                    : 0.f;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   }
   {
     TileCtx<NDIRS, PPT, SLOTS> cx;
-    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
+    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS, NTHR>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
     n = cx.n, t = cx.t, j = cx.j;
     if (!cx.ok) {
 #pragma unroll
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
     }
   }
   if (threadIdx.x < 3) amax_s[threadIdx.x] = 0u;
-  if (threadIdx.x < TL_MAXSLOW * NDIRS * 3) (&slowacc[0][0][0])[threadIdx.x] = 0.f;
+  for (int k = threadIdx.x; k < TL_MAXSLOW * NDIRS * 3; k += NTHR) (&slowacc[0][0][0])[k] = 0.f;
   bool has_bl[NDIRS];
   float blmax[PPT];
 #pragma unroll
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   for (int s = 0; s < SLOTS; ++s) {
     const int d = piece_dir(info[s]);
     tsel[s] = 8u * (unsigned)d;
-    const bool none = threadIdx.x + s * TL_THREADS >= total, zero = piece_zero(info[s]);
+    const bool none = threadIdx.x + s * NTHR >= total, zero = piece_zero(info[s]);
     poff[s] = none ? PIECE_NONE : zero ? PIECE_ZERO : piece_y(info[s]) * P.grp[g0].src_sh[d] + piece_col(info[s]);
     // no group has a grad_src for this direction <=> group g0 has none (host-checked): nothing to flush
     goff[s] = (none || zero || Q.grad_src[g0][d] == nullptr) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
@@ -790,9 +792,9 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   {
     const int nslow = slow.n;
     const int sh0 = P.grp[g0].src_sh[0], sh1 = P.grp[g0].src_sh[NDIRS - 1];
-    for (int it = threadIdx.x; it < nslow * Cn; it += TL_THREADS) {
+    for (int it = threadIdx.x; it < nslow * Cn; it += NTHR) {
       const int cf = it / nslow, sidx = it - cf * nslow, pix = slow.pix[sidx];  // lanes = different pixels: no same-address
-      const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
+      const int si = blockIdx.y * (4 * (NTHR / 128) * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
       const TileChanB& tc = tab[cf];
       const float gout = __ldg(tc.go + si * Q.go_sh[g0] + sj);
       float va[NDIRS][4];
@@ -891,7 +893,7 @@ __global__ void __launch_bounds__(TL_THREADS, PPT == 1 ? 3 : 2) bwd_tile_kernel(
   if (flush_prev) flush(Cn - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
   if (threadIdx.x < slow.n * NDIRS) {  // coordinate gradients of the slow pixels
     const int sidx = threadIdx.x / NDIRS, d = threadIdx.x - sidx * NDIRS, pix = slow.pix[sidx];
-    const int si = blockIdx.y * (8 * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
+    const int si = blockIdx.y * (4 * (NTHR / 128) * PPT) + (pix >> 5), sj = blockIdx.x * TL_TW + (pix & 31);
     Tap k;  // the full tap (gradient multipliers, raw flow, gate): only needed here
     compute_tap(G, P.dir[d], n, t, si, sj, k);
     bwdflow_store(P, Q, d, n, t, si, sj, k, slowacc[sidx][d][0], slowacc[sidx][d][1], slowacc[sidx][d][2]);
