@@ -16,6 +16,7 @@ from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 from ._problem import fill_grads, fill_problem
@@ -123,6 +124,7 @@ class _WarpBlendFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @once_differentiable  # the gradients are computed by CUDA kernels autograd cannot see through: no silent double backward
     def backward(ctx, *grad_outs):
         cfg: _Cfg = ctx.cfg
         D, G = cfg.n_dirs, cfg.n_groups
@@ -365,6 +367,7 @@ class _LabelWarpFn(torch.autograd.Function):
         return p
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, go):
         cfg: _Cfg = ctx.cfg
         D = cfg.n_dirs
@@ -509,6 +512,7 @@ class _MaskBlendFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, go: Tensor):
         inp, mask, noise = ctx.saved_tensors
         go = _wcontig(go)
