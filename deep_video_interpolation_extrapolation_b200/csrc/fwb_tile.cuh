@@ -41,6 +41,10 @@ constexpr int TL_ROWS_P = 96;                  // padded: 3 rows per lane in the
 constexpr int TL_ZPAD = 16;                    // zero cells in front of every stage (target of tap-less pixels)
 constexpr int TL_SK4 = 3;                      // row skew in pieces: cell (x, row r) sits at offset == x + 12 r (mod 32)
 constexpr bool TL_FILL_GAPS = false;           // A/B: fill the row placement gaps with real pieces (measured slower: 0.323 / 0.728 ms vs 0.304 / 0.680)
+#ifndef TL_SMOOTH_LEN4
+#define TL_SMOOTH_LEN4 10  // a tile whose widest row segment has at most this many 16-byte pieces counts as near-rigid
+#endif
+constexpr int TL_SK4_SMOOTH = 2;                // row skew (pieces) of near-rigid tiles
 constexpr int TL_AL4 = 8;                      // row placement period in 4-cell pieces: a staged cell of image column x sits at cell offset == x (mod 16)
 
 struct TilePix {  // per (pixel of this thread, direction)
@@ -104,8 +108,16 @@ __device__ __forceinline__ void tile_tab_scan(TileTab& tb, int slot_start4) {
     const bool has = lo <= hi;
     xs[h] = has ? ((lo >> 2) << 2) : 0;             // arithmetic shift: -1 -> -4
     ln[h] = has ? ((hi + 4) >> 2) - (lo >> 2) : 0;  // float4 pieces
-    ph[h] = ((xs[h] >> 2) + TL_SK4 * (3 * lane + h)) & (TL_AL4 - 1);
   }
+  // row skew per tile: near-rigid footprints (every row about as wide as the tile) are gathered conflict-free with a skew of
+  // 8 words (four rows of an 8x4 patch land on banks 0-7, 8-15, ...); stretched / sheared ones do best with 12
+  int sk4 = TL_SK4;
+  if (TL_SK4_SMOOTH != TL_SK4) {
+    const int widest = __reduce_max_sync(0xffffffffu, max(ln[0], max(ln[1], ln[2])));
+    if (widest <= TL_SMOOTH_LEN4) sk4 = TL_SK4_SMOOTH;
+  }
+#pragma unroll
+  for (int h = 0; h < 3; ++h) ph[h] = ((xs[h] >> 2) + sk4 * (3 * lane + h)) & (TL_AL4 - 1);
   // end phase of the last non-empty row before this lane's rows (empty rows take no space and no padding):
   // v = 8 | end phase of the lane's last non-empty row, 0 when all three are empty; inclusive "last valid" scan
   int v_e = 0;
