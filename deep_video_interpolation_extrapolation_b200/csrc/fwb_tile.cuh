@@ -439,6 +439,13 @@ __device__ __forceinline__ float* zero_plane(const ZeroP& Z, const Geo& G, int g
   if (!p || (t != 0 && Z.st[g][d] == 0)) return nullptr;  // a source shared by all T frames is cleared by the t == 0 tiles
   return p + n * Z.sn[g][d] + t * Z.st[g][d] + (long long)c * Z.sc[g][d];
 }
+#ifndef TL_ZFILL_BULK
+#define TL_ZFILL_BULK 0  // A/B: zero-fill by 1-D bulk copies (UBLKCP: shared zeros -> global rows) instead of LSU stores: 0.301 vs 0.305 ms, not worth it
+#endif
+// bytes (multiple of 16) of zeros from the CTA's shared zero line to global memory through the bulk-copy engine
+__device__ __forceinline__ void bulk_zero_row(float* gdst, unsigned zsrc_s, int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(zsrc_s), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void st_zero4_if(float* p, bool on) {
   asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %1, 0;\n @pp st.global.v4.f32 [%0], {%2,%2,%2,%2};\n}\n" ::"l"(p), "r"((int)on), "f"(0.f)
                : "memory");
@@ -452,6 +459,11 @@ __global__ void __launch_bounds__(TL_THREADS, TL_FWD_MINCTA) fwd_tile_kernel(con
   __shared__ StageSlow slow;
   __shared__ Tap slowtap[TL_MAXSLOW][NDIRS];
   __shared__ __align__(16) TileChanF tab[TL_MAXCH];
+  __shared__ __align__(128) float zline[TL_TW];  // 128 bytes of zeros: source of the bulk zero-fill
+  if (TL_ZFILL_BULK && Z.on && threadIdx.x < TL_TW) {
+    zline[threadIdx.x] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the bulk-copy engine (barriers follow in the prologue)
+  }
   int n, t, j, stage_f;
   bool act[TL_PPT];
   float w[TL_PPT][NDIRS][4], bl[TL_PPT][NDIRS];
@@ -546,7 +558,19 @@ __global__ void __launch_bounds__(TL_THREADS, TL_FWD_MINCTA) fwd_tile_kernel(con
     for (int p = 0; p < TL_FD - 1; ++p, so += stage_b) issue(p, so);
   }
   // zero-fill of the grad_src blocks (side job, Z.on): fire-and-forget stores while the first copies are in flight
-  if (zoff >= 0) {
+  if (TL_ZFILL_BULK) {
+    if (Z.on) {  // one bulk copy per (plane, row of the tile): 16 rows x 2 directions x Ctot planes spread over the threads
+      const unsigned zs = (unsigned)__cvta_generic_to_shared(zline);
+      const int j0 = blockIdx.x * TL_TW, i0z = blockIdx.y * TL_TH;
+      const int bytes = 4 * min(TL_TW, P.geo.W - j0);
+      for (int it = threadIdx.x; it < Ctot * NDIRS * TL_TH; it += TL_THREADS) {
+        const int row = it % TL_TH, pl = it / TL_TH, d = pl % NDIRS, cf = pl / NDIRS;
+        float* const zp = tab[cf].z[d];
+        if (zp != nullptr && i0z + row < P.geo.H) bulk_zero_row(zp + (i0z + row) * Z.sh[d] + j0, zs, bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else if (zoff >= 0) {
     unsigned tz = tab_s + 16u + zsel;
 #pragma unroll 4
     for (int cf = 0; cf < Ctot; ++cf, tz += (unsigned)sizeof(TileChanF)) {
@@ -589,6 +613,8 @@ __global__ void __launch_bounds__(TL_THREADS, TL_FWD_MINCTA) fwd_tile_kernel(con
     if (poffs == ring_b) poffs = 0;
     te += (unsigned)sizeof(TileChanF);
   }
+  // the bulk copies read this CTA's shared memory: they must have done so before the CTA exits
+  if (TL_ZFILL_BULK && Z.on) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
