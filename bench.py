@@ -332,6 +332,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     _lib.load()  # no fallback: fail loudly when the CUDA library is missing
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from deep_video_interpolation_extrapolation_b200 import sharding
+    numa_cores = sharding.bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa_bind) else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -509,7 +511,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
                               "frac": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
             "kernels": kernels,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "chunk": args.e2e_chunk,
+                    "chunk": args.e2e_chunk, "numa_local_cores": numa_cores,
                     "api": "deep_video_interpolation_extrapolation_b200.HostWarpBlend.run (forward + backward C-ABI calls per batch chunk; "
                            "pinned host in/out, H2D | compute | D2H on three streams)"},
             "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
@@ -553,6 +555,7 @@ def main():
                          "memsets, or a side stream (A/B)")
     ap.add_argument("--e2e-chunk", type=int, default=2, help="clips per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--aux", action="store_true", help="also time the mask-blend (refine) kernels")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")
     args = ap.parse_args()

@@ -99,3 +99,13 @@ def test_chunk_slices_cover_the_batch():
             assert all(0 < s.stop - s.start <= c for s in sl)
     with pytest.raises(ValueError):
         sharding.chunk_slices(4, 0)
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """bind_to_gpu_numa never raises: without NVML / a GPU it leaves the affinity alone and reports 0 cores."""
+    before = os.sched_getaffinity(0)
+    n = sharding.bind_to_gpu_numa(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
