@@ -773,3 +773,30 @@ def test_backward_without_some_source_gradients(pkg, oracle, which):
                 assert relerr(t.grad, rg["grad_srcs"][g][d][:, 0]) <= BWD_TOL
             else:
                 assert t.grad is None
+
+
+@pytest.mark.parametrize("det", [True, False])
+def test_c_abi_calls_are_cuda_graph_capturable(pkg, det):
+    """The entry points only launch kernels / memset nodes on the caller's stream (no allocation, no synchronisation), so a
+    forward+backward pair can be captured once and replayed: same bits as the eager launches in deterministic mode, within
+    the backward bar for the fused (reduction-order dependent) path."""
+    from deep_video_interpolation_extrapolation_b200.host_pipeline import _Slot
+    N, H, W = 2, 48, 64
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    kw = dict(padding_mode="border", align_corners=False, deterministic=det, tail=None)
+    slot = _Slot(torch.device("cuda:0"), N, (3, 20), H, W, kw)
+    for dst, src in zip(slot.inputs(), [*f0, *f1, ff, fb, mf, mb, *gos]):
+        dst.view(-1).copy_(cu(src).view(-1))
+    slot.launch(N, torch.cuda.current_stream().cuda_stream)  # eager (also warms up cudaFuncSetAttribute)
+    torch.cuda.synchronize()
+    eager = [t.clone() for t in slot.results()]
+    for t in slot.results():
+        t.fill_(float("nan"))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        slot.launch(N, torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, slot.results()):
+        assert torch.equal(a, b) if det else relerr(b, a) <= BWD_TOL
