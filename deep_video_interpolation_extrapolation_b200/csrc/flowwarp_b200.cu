@@ -806,6 +806,10 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
     if (ppt == 1) {                                                                               \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 1, 2>, sb))) return rc;                         \
       bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
+    } else if (!any_src) { /* flow-only backward: no accumulators, 3 CTAs/SM */                   \
+      const int sbn = env_int("FWB_TILE_BWDF_KB", 52) * 1024;                                     \
+      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false>, sbn))) return rc;     \
+      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false><<<grid, TL_THREADS, sbn, s>>>(P, Q, sbn / 4); \
     } else {                                                                                      \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3>, sb))) return rc;                         \
       bwd_tile_kernel<D, A, B, 2, 3><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \

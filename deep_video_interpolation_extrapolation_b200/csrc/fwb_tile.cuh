@@ -634,8 +634,10 @@ __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, i
   scatter_atomic_px(Q, g, d, n, t, c, false, k, gw, 0.f);
 }
 
-template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS>
-__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+// SCATTER = false: no grad_src is wanted (the sources are data): kernel 2 only on the staged tiles - no accumulators, no scale
+// vote, no flush; fewer registers and 4 instead of 6 shared-memory units per CTA, hence 3 CTAs per SM.
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS, bool SCATTER = true>
+__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER) ? 3 : 2)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
                                                                  int smem_floats) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
   }
   {
     TileCtx<NDIRS, PPT, SLOTS> cx;
-    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS, NTHR>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, TL_BD + 2, cx);
+    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS, NTHR>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, SCATTER ? TL_BD + 2 : TL_BD, cx);
     n = cx.n, t = cx.t, j = cx.j;
     if (!cx.ok) {
 #pragma unroll
@@ -758,7 +760,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
     const bool none = threadIdx.x + s * NTHR >= total, zero = piece_zero(info[s]);
     poff[s] = none ? PIECE_NONE : zero ? PIECE_ZERO : piece_y(info[s]) * P.grp[g0].src_sh[d] + piece_col(info[s]);
     // no group has a grad_src for this direction <=> group g0 has none (host-checked): nothing to flush
-    goff[s] = (none || zero || Q.grad_src[g0][d] == nullptr) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
+    goff[s] = (!SCATTER || none || zero || Q.grad_src[g0][d] == nullptr) ? PIECE_NONE : piece_y(info[s]) * Q.gs_sh[g0][d] + piece_col(info[s]);
   }
   int gooff[PPT];
 #pragma unroll
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
   float go[PPT], gn[PPT];
 #pragma unroll
   for (int q = 0; q < PPT; ++q) go[q] = (Cn > 0 && act[q]) ? ego[q] : 0.f;  // channel 0 (loaded before the prologue)
-  vote_amax(go, 0);
+  if (SCATTER) vote_amax(go, 0);
   // slow pixels, while the first copies are in flight: one (pixel, channel) item per thread, all loads of an item
   // independent (one exposed memory latency, the eight warps evenly loaded); the coordinate-gradient partial sums over
   // the channels meet in shared memory and are stored after the channel loop
@@ -873,10 +875,10 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
     __syncthreads();  // channel cf has landed; scatter of cf-1 complete; flush of cf-2 complete
     issue(cf + TL_BD - 1, poffs);
     load_go(cf + 1, gn);
-    if (threadIdx.x == 0) amax_s[(cf + 2) % 3] = 0u;
-    if (flush_prev) flush(cf - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
+    if (SCATTER && threadIdx.x == 0) amax_s[(cf + 2) % 3] = 0u;
+    if (SCATTER && flush_prev) flush(cf - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
     // ---- scale of this channel
-    const unsigned ab = amax_s[cf % 3];
+    const unsigned ab = SCATTER ? amax_s[cf % 3] : 0u;
     const bool finite = ab < 0x7f800000u;
     const int sexp = min(252, max(2, 274 - (int)(ab >> 23)));  // biased exponent of 2^(20 - exponent(amax))
     const float S = __uint_as_float((unsigned)sexp << 23);
@@ -885,7 +887,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
     const unsigned sb = smem_s + soff, ac = acc_s + aoff;
     bool want[NDIRS];
 #pragma unroll
-    for (int d = 0; d < NDIRS; ++d) want[d] = tc.gs[d] != nullptr;
+    for (int d = 0; d < NDIRS; ++d) want[d] = SCATTER && tc.gs[d] != nullptr;
     const float Sf = (finite && ab != 0u) ? S : 0.f;  // 0: nothing goes to the accumulator
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
@@ -916,7 +918,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : (PPT == 1 ? 3 : 2)) bw
         for (int d = 0; d < NDIRS; ++d)
           if (tc.gs[d] != nullptr && act[q]) bwd_nonfinite_px(P, Q, n, t, irow[q], j, tc.g, tc.c, d, has_bl[d] ? go[q] * bl[q][d] : go[q]);
     }
-    vote_amax(gn, (cf + 1) % 3);
+    if (SCATTER) vote_amax(gn, (cf + 1) % 3);
 #pragma unroll
     for (int q = 0; q < PPT; ++q) go[q] = gn[q];
     Sinv_prev = Sinv;
