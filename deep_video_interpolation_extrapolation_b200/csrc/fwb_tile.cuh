@@ -41,6 +41,9 @@ constexpr int TL_ROWS_P = 96;                  // padded: 3 rows per lane in the
 constexpr int TL_ZPAD = 16;                    // zero cells in front of every stage (target of tap-less pixels)
 constexpr int TL_SK4 = 3;                      // row skew in pieces: cell (x, row r) sits at offset == x + 12 r (mod 32)
 constexpr bool TL_FILL_GAPS = false;           // A/B: fill the row placement gaps with real pieces (measured slower: 0.323 / 0.728 ms vs 0.304 / 0.680)
+#ifndef TL_BWD_MINCTA
+#define TL_BWD_MINCTA 2  // resident CTAs per SM the scatter backward is compiled for (3 = 85 registers: measured below)
+#endif
 #ifndef TL_SMOOTH_LEN4
 #define TL_SMOOTH_LEN4 10  // a tile whose widest row segment has at most this many 16-byte pieces counts as near-rigid
 #endif
@@ -637,7 +640,7 @@ __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, i
 // SCATTER = false: no grad_src is wanted (the sources are data): kernel 2 only on the staged tiles - no accumulators, no scale
 // vote, no flush; fewer registers and 4 instead of 6 shared-memory units per CTA, hence 3 CTAs per SM.
 template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS, bool SCATTER = true>
-__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER) ? 3 : 2)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER) ? 3 : TL_BWD_MINCTA)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
                                                                  int smem_floats) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
