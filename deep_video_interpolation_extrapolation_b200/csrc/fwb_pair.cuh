@@ -535,6 +535,9 @@ __global__ void __launch_bounds__(PR_THREADS, 2) bwd_flow_pair_kernel(const __gr
 // The order of the global reductions varies from run to run: this is the NON-DETERMINISTIC mode; the
 // deterministic mode is kernel 2 followed by the owner gather (fwb_owner.cuh / fwb_csr.cuh).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -548,12 +551,29 @@ __device__ __forceinline__ void scatter_atomic_px(const GradP& Q, int g, int d, 
   gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d] + (long long)k.y0 * sh + k.x0;
   const float w[4] = {k.ux * k.uy, k.tx * k.uy, k.ux * k.ty, k.tx * k.ty};
   const int off[4] = {0, 1, sh, sh + 1};
+  // the (x0, x0+1) pair of a row goes out as ONE 8-byte vector reduction when both taps are inside the image and the pair
+  // is 8-byte aligned (half of the pixels when the strides are even): the L2 atomic units see 25 % fewer operations
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (k.valid & (1u << q)) {
-      atomicAdd(gs + off[q], w[q] * gw0);
-      if (two) atomicAdd(gs + off[q] + Q.gs_sc[g][d], w[q] * gw1);
+  for (int r = 0; r < 2; ++r) {
+    float* p0 = gs + off[2 * r];
+    const unsigned vv = (k.valid >> (2 * r)) & 3u;
+    if (vv == 3u && (reinterpret_cast<uintptr_t>(p0) & 7u) == 0u) {
+      red_add_v2(p0, w[2 * r] * gw0, w[2 * r + 1] * gw0);
+      if (two && (Q.gs_sc[g][d] & 1) == 0) {
+        red_add_v2(p0 + Q.gs_sc[g][d], w[2 * r] * gw1, w[2 * r + 1] * gw1);
+      } else if (two) {
+        atomicAdd(p0 + Q.gs_sc[g][d], w[2 * r] * gw1);
+        atomicAdd(p0 + Q.gs_sc[g][d] + 1, w[2 * r + 1] * gw1);
+      }
+    } else {
+#pragma unroll
+      for (int q = 2 * r; q < 2 * r + 2; ++q)
+        if (k.valid & (1u << q)) {
+          atomicAdd(gs + off[q], w[q] * gw0);
+          if (two) atomicAdd(gs + off[q] + Q.gs_sc[g][d], w[q] * gw1);
+        }
     }
+  }
 }
 
 // one pixel, all channels of all groups: kernel 2's generic body + global-atomic scatter (tiles that do not fit)
