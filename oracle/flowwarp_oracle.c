@@ -5,10 +5,10 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do, and
  * there only as the checker / the CPU baseline.  The product path is the CUDA library.
  *
- * Parity pin: the reference ships NO tests, golden vectors or fixtures for this path ("parity
- * unpinned" by the reference itself).  This restatement is therefore pinned
- * against outputs of the reference's own code run in the build container:
- * tests/golden/make_golden.py imports /root/reference/utils/net_utils.py unmodified, runs
+ * PARITY PIN (pinned): the reference ships no tests, golden vectors or fixtures of its own for this
+ * path, so this restatement is pinned to OUTPUTS OF THE UNMODIFIED REFERENCE run
+ * in the build container: tests/golden/make_golden.py (and make_golden_refine.py) import
+ * /root/reference/utils/net_utils.py as it is, run
  * FlowWrapper / warp / warp_back (+ autograd) on seeded inputs and stores the results in
  * tests/golden/ (npz files); tests/test_oracle_golden.py checks this file against them (exact sample
  * coordinates via the parity-image probe, outputs and gradients within the stated tolerances).
