@@ -210,7 +210,7 @@ def run_reference_arm(args, cfg, rank, world):
     }))
 
 
-def stock_torch_gpu_step(inp):
+def stock_torch_gpu_step(inp, return_leaves=False):
     """The composition the reference runs on its GPU today, restated inline (nothing imported from oracle/): base grid
     built on the CPU and sent to the device on every call (utils/net_utils.py:96-107), `grid = base -/+ flow` (:109-111),
     one F.grid_sample per modality and direction (:113, nets/VAE_S.py:134-135), mask weighting and sum
@@ -231,7 +231,25 @@ def stock_torch_gpu_step(inp):
             warped.append(F.grid_sample(x, grid, padding_mode="border", align_corners=False))
         outs.append(mf * warped[0] + mb * warped[1])
     torch.autograd.backward(outs, inp["gos"])
-    return outs
+    return (outs, leaves) if return_leaves else outs
+
+
+def parity_check(step, inp):
+    """--check: the buffers the timed loop just wrote (outputs and all gradients of the last step) against the stock torch
+    CUDA composition on the same inputs; max|a-b| / max|ref| per quantity."""
+    import torch
+    torch.cuda.synchronize()
+    ref_outs, leaves = stock_torch_gpu_step(inp, return_leaves=True)
+    G = len(inp["f0"])
+    rel = lambda a, r: float((a.reshape(r.shape).double() - r.double()).abs().max() / r.double().abs().max().clamp_min(1e-30))
+    res = {"fwd": max(rel(step.outs[g], ref_outs[g]) for g in range(G)),
+           "gsrc": max(rel(step.g_srcs[g][d], leaves[d * G + g].grad) for g in range(G) for d in range(2)),
+           "gflow": max(rel(step.g_flows[d], leaves[2 * G + d].grad) for d in range(2)),
+           "gmask": max(rel(step.g_blends[d], leaves[2 * G + 2 + d].grad) for d in range(2)),
+           "against": "stock torch CUDA composition (F.grid_sample + autograd) on the timed inputs",
+           "bars": {"fwd": 1e-6, "bwd": 1e-5}}
+    res["ok"] = bool(res["fwd"] <= 1e-6 and max(res["gsrc"], res["gflow"], res["gmask"]) <= 1e-5)
+    return res
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
@@ -375,6 +393,10 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     el = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)  # the job's step time is the slowest rank's device time
     value = sharding.job_throughput(pix_step, args.steps, el, world) / 1e9
 
+    # ---- --check (default on): the buffers the timed loop just wrote against the stock torch CUDA composition
+    pcheck = None
+    if not args.no_check and not args.profile and chain == 1:
+        pcheck = parity_check(step, inp)
     if args.profile:
         if sampler:
             sampler.stop()
@@ -517,6 +539,8 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
             "clocks": clocks,
         }
+        if pcheck is not None:
+            out["parity_check"] = pcheck
         if aux:
             out["aux_kernels"] = aux
         if variants:
@@ -557,6 +581,8 @@ def main():
     ap.add_argument("--aux", action="store_true", help="also time the mask-blend (refine) kernels")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--check", action="store_true", help="(default) compare the timed buffers with the stock torch CUDA composition")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity_check of the timed buffers")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

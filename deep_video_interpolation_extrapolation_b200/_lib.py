@@ -103,6 +103,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_
 SYMBOLS = (
     "fwb_version",
     "fwb_strerror",
+    "fwb_reload_env",
     "fwb_warp_blend_forward",
     "fwb_warp_blend_forward_zero",
     "fwb_label_warp_blend_forward",
@@ -136,6 +137,8 @@ def load() -> C.CDLL:
     pp, gp, vp = C.POINTER(fwb_problem), C.POINTER(fwb_grads), C.c_void_p
     lib.fwb_version.restype = C.c_int32
     lib.fwb_version.argtypes = []
+    lib.fwb_reload_env.restype = None
+    lib.fwb_reload_env.argtypes = []
     lib.fwb_strerror.restype = C.c_char_p
     lib.fwb_strerror.argtypes = [C.c_int32]
     lib.fwb_warp_blend_forward.restype = C.c_int32

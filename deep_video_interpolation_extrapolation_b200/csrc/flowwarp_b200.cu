@@ -11,13 +11,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "../../include/flowwarp_b200.h"
 #include "fwb_coords.cuh"
 #include "fwb_generic.cuh"
 #include "fwb_owner.cuh"
-#include "fwb_stage.cuh"
-#include "fwb_pair.cuh"
-#include "fwb_csr.cuh"
 #include "fwb_tile.cuh"
 #include "fwb_blend.cuh"
 #include "fwb_label.cuh"
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(NTHREADS) bwd_src_atomic_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static bool stride_ok(long long C, long long sc, long long H, long long sh);
 static int validate(const fwb_problem* p) {
   if (!p) return FWB_E_NULL;
   if (p->N < 0 || p->T < 1 || p->H < 1 || p->W < 1) return FWB_E_SHAPE;
@@ -174,10 +176,9 @@ static int validate(const fwb_problem* p) {
       if (!R->src[d]) return FWB_E_NULL;
       if ((uintptr_t)R->src[d] & 3u) return FWB_E_ALIGN;
       // in-image offsets are 32-bit in the kernels
-      if ((long long)R->C * R->src_sc[d] + (long long)(p->H + 2) * R->src_sh[d] > 2147483647LL ||
-          R->src_sc[d] < 0 || R->src_sh[d] < 0)
-        return FWB_E_SHAPE;
+      if (!stride_ok(R->C, R->src_sc[d], p->H, R->src_sh[d])) return FWB_E_SHAPE;
     }
+    if (R->out && !stride_ok(R->C, R->out_sc, p->H, R->out_sh)) return FWB_E_SHAPE;
   }
   return 0;
 }
@@ -232,8 +233,19 @@ static void to_params(const fwb_problem* p, Params& P) {
   }
 }
 
+// in-plane offsets are 32-bit in the kernels: a channel / row stride must be non-negative and the farthest in-plane offset
+// (C channels, H + 2 rows) must fit
+static bool stride_ok(long long C, long long sc, long long H, long long sh) {
+  return sc >= 0 && sh >= 0 && sc <= 2147483647LL && sh <= 2147483647LL && C * sc + (H + 2) * sh <= 2147483647LL;
+}
+
 static int to_grads(const fwb_problem* p, const fwb_grads* q, GradP& Q) {
   if (!q) return FWB_E_NULL;
+  for (int g = 0; g < p->n_groups; ++g) {
+    if (q->grad_out[g] && !stride_ok(p->grp[g].C, q->go_sc[g], p->H, q->go_sh[g])) return FWB_E_SHAPE;
+    for (int d = 0; d < p->n_dirs; ++d)
+      if (q->grad_src[g][d] && !stride_ok(p->grp[g].C, q->gs_sc[g][d], p->H, q->gs_sh[g][d])) return FWB_E_SHAPE;
+  }
   for (int g = 0; g < FWB_MAX_GROUPS; ++g) {
     const bool on = g < p->n_groups;
     Q.grad_out[g] = on ? q->grad_out[g] : nullptr;
@@ -274,36 +286,49 @@ static dim3 pixel_grid(const fwb_problem* p) {
   return dim3((p->W + BX - 1) / BX, (p->H + BY - 1) / BY, p->N * p->T);
 }
 
-static dim3 stage_grid(const fwb_problem* p) {
-  return dim3((p->W + PR_TW - 1) / PR_TW, (p->H + PR_TH - 1) / PR_TH, p->N * p->T);
-}
-
-// Kernel selection.  Defaults are the fastest measured variants (DESIGN.md "Kernel variants"):
-//   forward            generic one-thread-per-pixel gather           ("pairfwd": shared-memory channel-pair kernel)
-//   backward, fast     kernels 2+3 fused, shared-memory tiles + RED   ("nofuse": split kernels, atomics-free)
-//   backward, determ.  generic kernel 2 + owner-gather kernel 3       ("pairflow": channel-pair kernel 2, "csr": list kernel 3)
-// FWB_KERNELS=<comma separated words> switches variants for A/B measurements and for the tests that keep every
-// variant parity-checked; read on every call (getenv is cheap next to a launch).
-enum : unsigned { KN_PAIRFWD = 1u, KN_PAIRFLOW = 2u, KN_CSR = 4u, KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_PAIRBWD = 64u, KN_NOZFUSE = 128u };
-static unsigned knobs() {
-  const char* v = getenv("FWB_KERNELS");
-  if (!v || !*v) return 0u;
-  unsigned k = 0u;
-  if (strstr(v, "pairfwd")) k |= KN_PAIRFWD;
-  if (strstr(v, "pairflow")) k |= KN_PAIRFLOW;
-  if (strstr(v, "csr")) k |= KN_CSR;
-  if (strstr(v, "nofuse")) k |= KN_NOFUSE;
-  if (strstr(v, "generic")) k |= KN_GENERIC;
-  if (strstr(v, "notile")) k |= KN_NOTILE;
-  if (strstr(v, "pairbwd")) k |= KN_PAIRBWD;
-  if (strstr(v, "nozfuse")) k |= KN_NOZFUSE;
-  return k;
-}
+// Kernel selection.  Defaults are the fastest measured variants:
+//   forward            shared-memory tile kernel (fwb_tile.cuh)              ("notile" / "generic": one-thread-per-pixel gather)
+//   backward, fast     kernels 2+3 fused on tiles, shared accumulators + RED  ("nofuse": split kernels, atomics-free)
+//   backward, determ.  generic kernel 2 + owner-gather kernel 3
+// FWB_KERNELS=<comma separated words> and the FWB_TILE_* sizes switch variants for A/B measurements and for the tests that
+// keep every variant parity-checked.  The environment is read ONCE per process (thread-safe); fwb_reload_env() re-reads it.
+enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u };
+struct EnvCfg {
+  unsigned knobs;
+  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwd_ppt;
+};
+static EnvCfg g_env;
+static std::atomic<int> g_env_ready{0};
+static std::mutex g_env_mu;
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
-static int stage_smem_bytes() { return env_int("FWB_SMEM_KB", 62) * 1024; }
+static void env_load_locked() {
+  EnvCfg e;
+  e.knobs = 0u;
+  const char* v = getenv("FWB_KERNELS");
+  if (v && *v) {
+    if (strstr(v, "nofuse")) e.knobs |= KN_NOFUSE;
+    if (strstr(v, "generic")) e.knobs |= KN_GENERIC;
+    if (strstr(v, "notile")) e.knobs |= KN_NOTILE;
+    if (strstr(v, "nozfuse")) e.knobs |= KN_NOZFUSE;
+  }
+  e.tile_bwd_ppt = env_int("FWB_TILE_BWD_PPT", 2);
+  e.tile_fwd_kb = env_int("FWB_TILE_FWD_KB", 52);
+  e.tile_bwd_kb = env_int("FWB_TILE_BWD_KB", e.tile_bwd_ppt == 1 ? 48 : 80);
+  e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
+  g_env = e;
+  g_env_ready.store(1, std::memory_order_release);
+}
+static const EnvCfg& env() {
+  if (!g_env_ready.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(g_env_mu);
+    if (!g_env_ready.load(std::memory_order_relaxed)) env_load_locked();
+  }
+  return g_env;
+}
+static unsigned knobs() { return env().knobs; }
 static bool force_generic() { return (knobs() & KN_GENERIC) != 0u; }
 
 // the staged kernels move 16-byte pieces of the source planes with cp.async: every source pointer must be
@@ -365,9 +390,33 @@ static bool tile_bwd_ok(const fwb_problem* p, const fwb_grads* q) {
   return (long long)(p->H + 1) * q->go_sh[g0] < 2147483647LL;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(kernel, device) attribute: set it only when a launch needs more than
+// what this process already asked for on the current device (one cudaFuncSetAttribute per kernel and device, not per launch)
+struct SmemAttr {
+  const void* fn;
+  int dev, bytes;
+};
+static std::mutex g_attr_mu;
+static std::vector<SmemAttr> g_attr;
+static int set_smem_ptr(const void* fn, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  for (SmemAttr& a : g_attr)
+    if (a.fn == fn && a.dev == dev) {
+      if (a.bytes >= bytes) return 0;
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e == cudaSuccess) a.bytes = bytes;
+      return (int)e;
+    }
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) g_attr.push_back({fn, dev, bytes});
+  return (int)e;
+}
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return set_smem_ptr(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 }  // namespace fwb
@@ -412,41 +461,7 @@ static int32_t run_backward_src(const fwb_problem* p, const fwb_grads* g, void* 
     const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
     if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 15u)) return FWB_E_WORKSPACE;
     const WsView ws = ws_view(workspace, L, NT, p->H, p->W);
-    if (knobs() & KN_CSR) {
-      // ---- owner gather over contributor lists (fwb_csr.cuh)
-      const int dyn = env_int("FWB_CSR_KB", 110) * 1024;
-      if ((size_t)dyn < csr_smem_bytes(0)) return FWB_E_WORKSPACE;
-      if ((rc = set_smem(bwd_src_csr_kernel, dyn))) return rc;
-      for (int d = 0; d < p->n_dirs; ++d)
-        for (int shared = 0; shared < 2; ++shared) {
-          CsrArgs A = {};
-          A.d = d;
-          A.tshared = shared;
-          A.gout_vec = force_generic() ? 0 : 1;
-          A.stage_floats = (int)((dyn - csr_fixed_bytes()) / 4);
-          A.long_len = min(31, max(2, env_int("FWB_CSR_LONG", 28)));
-          for (int gi = 0; gi < p->n_groups; ++gi) {
-            if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
-            const int is_shared = (Q.gs_st[gi][d] == 0 && p->T > 1) ? 1 : 0;
-            if (is_shared != shared) continue;
-            A.group_mask |= 1u << gi;
-            if (((uintptr_t)Q.grad_out[gi] & 15u) || (Q.go_sn[gi] & 3) || (Q.go_st[gi] & 3) || (Q.go_sc[gi] & 3) ||
-                (Q.go_sh[gi] & 3))
-              A.gout_vec = 0;
-          }
-          if (!A.group_mask) continue;
-          const dim3 grid((p->W + CS_TW - 1) / CS_TW, (p->H + CS_TH - 1) / CS_TH, shared ? p->N : NT);
-          bwd_src_csr_kernel<<<grid, CS_THREADS, dyn, s>>>(P, Q, ws, A);
-          if ((rc = (int32_t)cudaGetLastError())) return rc;
-        }
-    } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(bwd_src_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)own_smem_bytes(OWN_MAXGRP));
-      if (e != cudaSuccess) return (int32_t)e;
-      attr_set = true;
-    }
+    if ((rc = set_smem(bwd_src_owner_kernel, (int)own_smem_bytes(OWN_MAXGRP)))) return rc;
     for (int d = 0; d < p->n_dirs; ++d)
       for (int shared = 0; shared < 2; ++shared) {
         // channel runs of the groups that want grad_src for this direction with this T-sharing,
@@ -483,7 +498,6 @@ static int32_t run_backward_src(const fwb_problem* p, const fwb_grads* g, void* 
         }
         if ((rc = flush())) return rc;
       }
-    }
     // a group whose grad_out is NULL contributes nothing: its grad_src is zero
     for (int gi = 0; gi < p->n_groups; ++gi)
       for (int d = 0; d < p->n_dirs; ++d)
@@ -517,6 +531,11 @@ extern "C" {
 
 int32_t fwb_version(void) { return FWB_VERSION; }
 
+void fwb_reload_env(void) {
+  std::lock_guard<std::mutex> lk(g_env_mu);
+  env_load_locked();
+}
+
 const char* fwb_strerror(int32_t code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   switch (code) {
@@ -549,7 +568,7 @@ static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stre
   if (zq && (rc = to_grads(p, zq, Q))) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tile = !(knobs() & (KN_PAIRFWD | KN_NOTILE)) && stage_ok(p) && tile_fwd_ok(p);
+  const bool tile = !(knobs() & KN_NOTILE) && stage_ok(p) && tile_fwd_ok(p);
   ZeroP Z;
   memset(&Z, 0, sizeof(Z));
   if (zq) {
@@ -575,7 +594,7 @@ static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stre
     if (any && !Z.on && (rc = zero_grad_src(p, Q, s))) return rc;
   }
   if (tile) {
-    const int sb = env_int("FWB_TILE_FWD_KB", 52) * 1024;
+    const int sb = env().tile_fwd_kb * 1024;
     const int Ctot = total_channels(p);
     const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + TL_TH - 1) / TL_TH, p->N * p->T);
 #define FWB_LAUNCH_TFWD(D, A, B)                                                     \
@@ -595,27 +614,6 @@ static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stre
       default: FWB_LAUNCH_TFWD(2, true, true); break;
     }
 #undef FWB_LAUNCH_TFWD
-    return (int32_t)cudaGetLastError();
-  }
-  if ((knobs() & KN_PAIRFWD) && stage_ok(p)) {
-    const int sb = stage_smem_bytes();
-#define FWB_LAUNCH_FWD(D, A, B)                                                      \
-  do {                                                                               \
-    if ((rc = set_smem(fwd_pair_kernel<D, A, B>, sb))) return rc;                    \
-    fwd_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, sb / 4);       \
-  } while (0)
-    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
-    switch (key) {
-      case 0: FWB_LAUNCH_FWD(1, false, false); break;
-      case 1: FWB_LAUNCH_FWD(1, false, true); break;
-      case 2: FWB_LAUNCH_FWD(1, true, false); break;
-      case 3: FWB_LAUNCH_FWD(1, true, true); break;
-      case 4: FWB_LAUNCH_FWD(2, false, false); break;
-      case 5: FWB_LAUNCH_FWD(2, false, true); break;
-      case 6: FWB_LAUNCH_FWD(2, true, false); break;
-      default: FWB_LAUNCH_FWD(2, true, true); break;
-    }
-#undef FWB_LAUNCH_FWD
     return (int32_t)cudaGetLastError();
   }
   const dim3 grid = pixel_grid(p), block(NTHREADS);
@@ -781,10 +779,14 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   const int NT = p->N * p->T;
   const bool fused_req = (p->flags & FWB_FLAG_FUSED_BWD) && !(p->flags & (FWB_FLAG_DETERMINISTIC | FWB_FLAG_ATOMIC_SRC));
   if (fused_req) {
-    bool any_src = false, ok = stage_ok(p) && !(knobs() & KN_NOFUSE);
+    // any_src: a group wants grad_src AND has a grad_out (it scatters); any_gs: some grad_src plane exists at all (a plane
+    // whose group has no grad_out still has to come back as zeros)
+    bool any_src = false, any_gs = false, ok = stage_ok(p) && !(knobs() & KN_NOFUSE);
     for (int gi = 0; gi < p->n_groups; ++gi)
       for (int d = 0; d < p->n_dirs; ++d) {
-        if (!Q.grad_src[gi][d] || !Q.grad_out[gi]) continue;
+        if (!Q.grad_src[gi][d]) continue;
+        any_gs = true;
+        if (!Q.grad_out[gi]) continue;
         any_src = true;
         if (((uintptr_t)Q.grad_src[gi][d] & 15u) || (Q.gs_sn[gi][d] & 3) || (Q.gs_st[gi][d] & 3) || (Q.gs_sc[gi][d] & 3) ||
             (Q.gs_sh[gi][d] & 3))
@@ -792,14 +794,14 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
       }
     // a backward without any grad_src (the sources are data: the usual training case) takes the tile kernel too: it then
     // neither scatters nor flushes, i.e. it is kernel 2 on the staged tiles
-    const bool tile_ok = !(knobs() & (KN_PAIRBWD | KN_NOTILE)) && tile_bwd_ok(p, g);
-    if (ok && (any_src || tile_ok)) {
-      // grad_src is accumulated with reductions: zero it first (also the planes of groups without grad_out) unless the
+    const bool tile_ok = !(knobs() & KN_NOTILE) && tile_bwd_ok(p, g);
+    if (ok && tile_ok) {
+      // grad_src is accumulated with reductions: zero every plane first (also those of groups without grad_out) unless the
       // caller did (FWB_FLAG_GRAD_SRC_ZEROED, e.g. fwb_warp_blend_forward_zero)
-      if (any_src && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
+      if (any_gs && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
       if (tile_ok) {
-        const int ppt = env_int("FWB_TILE_BWD_PPT", 2);  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
-        const int sb = env_int("FWB_TILE_BWD_KB", ppt == 1 ? 48 : 80) * 1024;
+        const int ppt = env().tile_bwd_ppt;  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
+        const int sb = env().tile_bwd_kb * 1024;
         const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);
 #define FWB_LAUNCH_TBWD(D, A, B)                                                                  \
   do {                                                                                            \
@@ -807,7 +809,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 1, 2>, sb))) return rc;                         \
       bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
     } else if (!any_src) { /* flow-only backward: no accumulators, 3 CTAs/SM */                   \
-      const int sbn = env_int("FWB_TILE_BWDF_KB", 52) * 1024;                                     \
+      const int sbn = env().tile_bwdf_kb * 1024;                                     \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false>, sbn))) return rc;     \
       bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false><<<grid, TL_THREADS, sbn, s>>>(P, Q, sbn / 4); \
     } else {                                                                                      \
@@ -829,29 +831,9 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
 #undef FWB_LAUNCH_TBWD
         return (int32_t)cudaGetLastError();
       }
-      if (any_src) {
-      const int sb = env_int("FWB_FUSED_KB", 100) * 1024;
-#define FWB_LAUNCH_FUSED(D, A, B)                                                        \
-  do {                                                                                   \
-    if ((rc = set_smem(bwd_fused_pair_kernel<D, A, B>, sb))) return rc;                  \
-    bwd_fused_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
-  } while (0)
-      const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
-      switch (key) {
-        case 0: FWB_LAUNCH_FUSED(1, false, false); break;
-        case 1: FWB_LAUNCH_FUSED(1, false, true); break;
-        case 2: FWB_LAUNCH_FUSED(1, true, false); break;
-        case 3: FWB_LAUNCH_FUSED(1, true, true); break;
-        case 4: FWB_LAUNCH_FUSED(2, false, false); break;
-        case 5: FWB_LAUNCH_FUSED(2, false, true); break;
-        case 6: FWB_LAUNCH_FUSED(2, true, false); break;
-        default: FWB_LAUNCH_FUSED(2, true, true); break;
-      }
-#undef FWB_LAUNCH_FUSED
-      return (int32_t)cudaGetLastError();
-      }
     }
   }
+  // (not fused, or the tile kernel cannot take this problem: split path — kernel 2, then kernel 3 below)
   // the segment tables kernel 3 needs are produced whenever a workspace is supplied
   if (workspace && !(p->flags & FWB_FLAG_ATOMIC_SRC)) {
     const WsLayout L = ws_layout(p->n_dirs, NT, p->H, p->W);
@@ -867,26 +849,7 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   }
   int want = 0;
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
-  if (want && (knobs() & KN_PAIRFLOW) && stage_ok(p)) {
-    const int sb = stage_smem_bytes();
-#define FWB_LAUNCH_BWF(D, A, B)                                                         \
-  do {                                                                                  \
-    if ((rc = set_smem(bwd_flow_pair_kernel<D, A, B>, sb))) return rc;                  \
-    bwd_flow_pair_kernel<D, A, B><<<stage_grid(p), PR_THREADS, sb, s>>>(P, Q, sb / 4);  \
-  } while (0)
-    const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
-    switch (key) {
-      case 0: FWB_LAUNCH_BWF(1, false, false); break;
-      case 1: FWB_LAUNCH_BWF(1, false, true); break;
-      case 2: FWB_LAUNCH_BWF(1, true, false); break;
-      case 3: FWB_LAUNCH_BWF(1, true, true); break;
-      case 4: FWB_LAUNCH_BWF(2, false, false); break;
-      case 5: FWB_LAUNCH_BWF(2, false, true); break;
-      case 6: FWB_LAUNCH_BWF(2, true, false); break;
-      default: FWB_LAUNCH_BWF(2, true, true); break;
-    }
-#undef FWB_LAUNCH_BWF
-  } else if (want) {
+  if (want) {
     const dim3 grid = pixel_grid(p), block(NTHREADS);
     if (p->n_dirs == 2)
       bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);

@@ -3,7 +3,7 @@
 //
 // A CTA owns a 32x16 tile of output pixels of one (n, t): 8 warps, warp w owns rows w and w+8, lane = column.
 // The prologue computes everything that does not depend on the channel — taps, bilinear weights, the tile's
-// row-segment footprint (fwb_stage.cuh) for both directions, which 16-byte pieces of that footprint each
+// row-segment footprint for both directions, which 16-byte pieces of that footprint each
 // thread copies, the offsets of each pixel's taps inside the staged footprint — and keeps it in registers.
 // The channel loop is then a cp.async ring (TL_FD / TL_BD stages, ONE __syncthreads per channel):
 //     wait own copies of channel c | barrier | issue copies of channel c+D-1 | gather channel c from smem
@@ -18,8 +18,8 @@
 #pragma once
 #include "fwb_coords.cuh"
 #include "fwb_generic.cuh"
-#include "fwb_stage.cuh"
-#include "fwb_pair.cuh"
+#include "fwb_util.cuh"
+#include "fwb_tex.cuh"
 
 namespace fwb {
 
@@ -417,17 +417,6 @@ struct TileChanF {
   float* z[2];  // grad_src plane of this channel per direction to zero-fill (NULL: none), see ZeroP
 };
 
-// Optional side job of the forward: zero-fill the grad_src planes the fused backward will accumulate into.  Every tile
-// clears the 32x16 block of its own output coordinates in every plane (one 16-byte store per thread and channel, riding
-// on the forward's spare store bandwidth), so the backward needs no memset pass between the two kernels.
-struct ZeroP {
-  float* gs[FWB_MAX_GROUPS][2];
-  long long sn[FWB_MAX_GROUPS][2], st[FWB_MAX_GROUPS][2];
-  int sc[FWB_MAX_GROUPS][2];
-  int sh[2];  // row stride per direction (all groups agree, host-checked)
-  int on;
-};
-
 // element offset inside a grad_src plane of the 4 floats thread `tid` clears for direction *zd, or -1
 template <int NDIRS>
 __device__ __forceinline__ int zero_plan(const Geo& G, const ZeroP& Z, int* zd) {
@@ -436,11 +425,6 @@ __device__ __forceinline__ int zero_plan(const Geo& G, const ZeroP& Z, int* zd) 
   if (!Z.on || *zd >= NDIRS) return -1;
   const int i = blockIdx.y * TL_TH + ((tid >> 3) & 15), j = blockIdx.x * TL_TW + (tid & 7) * 4;
   return (i < G.H && j < G.W) ? i * Z.sh[*zd] + j : -1;
-}
-__device__ __forceinline__ float* zero_plane(const ZeroP& Z, const Geo& G, int g, int d, int n, int t, int c) {
-  float* p = Z.gs[g][d];
-  if (!p || (t != 0 && Z.st[g][d] == 0)) return nullptr;  // a source shared by all T frames is cleared by the t == 0 tiles
-  return p + n * Z.sn[g][d] + t * Z.st[g][d] + (long long)c * Z.sc[g][d];
 }
 #ifndef TL_ZFILL_BULK
 #define TL_ZFILL_BULK 0  // A/B: zero-fill by 1-D bulk copies (UBLKCP: shared zeros -> global rows) instead of LSU stores: 0.301 vs 0.305 ms, not worth it
@@ -634,7 +618,7 @@ struct TileChanB {
 __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, int n, int t, int i, int j, int g, int c, int d, float gw) {
   Tap k;
   compute_tap(P.geo, P.dir[d], n, t, i, j, k);
-  scatter_atomic_px(Q, g, d, n, t, c, false, k, gw, 0.f);
+  scatter_atomic_px(Q, g, d, n, t, c, k, gw);
 }
 
 // SCATTER = false: no grad_src is wanted (the sources are data): kernel 2 only on the staged tiles - no accumulators, no scale
@@ -861,7 +845,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
         }
         atomicAdd(&slowacc[sidx][d][0], gw * fmaf(k.ty, dd - cc, k.uy * (b - a)));
         atomicAdd(&slowacc[sidx][d][1], gw * fmaf(k.tx, dd - b, k.ux * (cc - a)));
-        scatter_atomic_px(Q, tc.g, d, n, t, tc.c, false, k, gw, 0.f);
+        scatter_atomic_px(Q, tc.g, d, n, t, tc.c, k, gw);
       }
     }
   }

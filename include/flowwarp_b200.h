@@ -21,7 +21,11 @@
  *   - logical batch is (N, T): T = opt.vid_length frames that share one launch.  A tensor that is
  *     shared by all T frames (the single source frame of warp()) passes a T-stride of 0.
  *   - every function launches asynchronously on `stream` (a cudaStream_t passed as void*), allocates
- *     nothing, keeps no global mutable state, never throws and never aborts.
+ *     nothing, never throws and never aborts.  Process-wide state is limited to two caches, both mutex-guarded: the A/B
+ *     environment knobs (FWB_KERNELS, FWB_TILE_*: read once, fwb_reload_env() re-reads) and the per-(kernel, device)
+ *     record of the dynamic shared-memory attribute already requested from the CUDA runtime.
+ *   - limits: N*T <= 65535 (grid.z), H, W <= 32767, every in-plane offset (C*channel stride + (H+2)*row stride) < 2^31
+ *     for sources, outputs and gradients; violations return FWB_E_SHAPE / FWB_E_RANGE.
  *   - return value: 0 = ok; > 0 = a cudaError_t from a launch; < 0 = FWB_E_* argument error.
  *   - sampling arithmetic (bit-exact contract, see DESIGN.md "Coordinate arithmetic"):
  *        bx[j]   = linspace(-1,1,W)[j]  (CPU torch.linspace bit pattern; -1 when W == 1)
@@ -51,7 +55,7 @@ extern "C" {
 #define FWB_PAD_BORDER 1
 
 /* flags */
-#define FWB_FLAG_DETERMINISTIC 1u /* grad_src must be bit-exact run to run (the default owner-gather kernel is) */
+#define FWB_FLAG_DETERMINISTIC 1u /* grad_src must be bit-exact run to run (kernel 3 as an owner gather, fwb_owner.cuh) */
 #define FWB_FLAG_ATOMIC_SRC 2u    /* grad_src by global atomics (ATen-style scatter; non-deterministic; for A/B runs) */
 #define FWB_FLAG_FUSED_BWD 4u     /* fwb_warp_blend_backward_flow also produces grad_src (kernels 2+3 fused: shared-memory
                                    * fixed-point tiles + vector reductions, non-deterministic); fwb_warp_blend_backward_src
@@ -180,6 +184,10 @@ int32_t fwb_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */
 const char* fwb_strerror(int32_t code);
+
+/* Re-read the A/B environment knobs (FWB_KERNELS, FWB_TILE_*).  They are otherwise read once per process.  Test / A-B hook:
+ * do not call it while another thread is inside a launch function. */
+void fwb_reload_env(void);
 
 /* Kernel 1 — fused forward: flow->coordinate, floor/fraction, validity, 4-tap bilinear gather
  * over every channel of every group, for 1 or 2 directions, and the blend-weighted sum.

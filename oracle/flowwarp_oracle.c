@@ -331,3 +331,74 @@ static void backward_batch(const void* arg, int begin, int end) {
               q->grad_blend[d][n * q->gb_sn[d] + t * q->gb_st[d] + i * q->gb_sh[d] + j] = gbl;
           }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Flat entry point for the full-size parity tests: contiguous fp32 arrays, plain pointers and sizes.
+ * The problem description is packed HERE, in C, from the shapes alone — it does not go through the
+ * product's Python struct packer (_problem.py), so a packing bug on the product side cannot cancel
+ * out in a CUDA-vs-oracle comparison.  The bidirectional warp + mask-weighted blend of
+ * nets/OpticalUnet.py:123-146 (direction 0: grid = base - flow0, direction 1: grid = base + flow1),
+ * T = 1, n_groups channel groups that share flows and blend masks.
+ *   src0[g], src1[g]   [N, C[g], H, W]      flow0, flow1   [N, 2, H, W]     blend0, blend1  [N, H, W] or NULL
+ *   out[g]             [N, C[g], H, W]      (forward; skipped when out == NULL)
+ *   gout[g]            [N, C[g], H, W]      (backward; skipped when gout == NULL)
+ *   gsrc0[g], gsrc1[g] [N, C[g], H, W]      gflow0, gflow1 [N, 2, H, W]     gblend0, gblend1 [N, H, W]
+ * ------------------------------------------------------------------------------------------- */
+int32_t fwo_bidir_contig(int32_t N, int32_t H, int32_t W, int32_t n_groups, const int32_t* C,
+                         const float* const* src0, const float* const* src1, const float* flow0,
+                         const float* flow1, const float* blend0, const float* blend1, int32_t pad,
+                         int32_t align_corners, float* const* out, const float* const* gout,
+                         float* const* gsrc0, float* const* gsrc1, float* gflow0, float* gflow1,
+                         float* gblend0, float* gblend1) {
+  if (n_groups < 1 || n_groups > FWB_MAX_GROUPS) return FWB_E_GROUPS;
+  fwb_problem p;
+  fwb_grads q;
+  memset(&p, 0, sizeof p);
+  memset(&q, 0, sizeof q);
+  const int64_t HW = (int64_t)H * W;
+  p.N = N, p.T = 1, p.H = H, p.W = W;
+  p.n_dirs = 2, p.n_groups = n_groups;
+  p.padding_mode = pad, p.align_corners = align_corners, p.flags = 0;
+  const float* flows[2] = {flow0, flow1};
+  const float* blends[2] = {blend0, blend1};
+  float* gflows[2] = {gflow0, gflow1};
+  float* gblends[2] = {gblend0, gblend1};
+  for (int d = 0; d < 2; ++d) {
+    p.dir[d].flow = flows[d];
+    p.dir[d].flow_sn = 2 * HW, p.dir[d].flow_sc = HW, p.dir[d].flow_st = 0, p.dir[d].flow_sh = W;
+    p.dir[d].blend = blends[d];
+    p.dir[d].blend_sn = HW, p.dir[d].blend_st = 0, p.dir[d].blend_sh = W;
+    p.dir[d].sign = d == 0 ? -1.0f : 1.0f;
+    q.grad_flow[d] = gflows[d];
+    q.gf_sn[d] = 2 * HW, q.gf_sc[d] = HW, q.gf_st[d] = 0, q.gf_sh[d] = W;
+    q.grad_blend[d] = gblends[d];
+    q.gb_sn[d] = HW, q.gb_st[d] = 0, q.gb_sh[d] = W;
+  }
+  for (int g = 0; g < n_groups; ++g) {
+    fwb_group* G = &p.grp[g];
+    G->C = C[g];
+    const float* s[2] = {src0[g], src1[g]};
+    for (int d = 0; d < 2; ++d) {
+      G->src[d] = s[d];
+      G->src_sn[d] = C[g] * HW, G->src_st[d] = 0, G->src_sc[d] = HW, G->src_sh[d] = W;
+    }
+    if (out) {
+      G->out = out[g];
+      G->out_sn = C[g] * HW, G->out_st = 0, G->out_sc = HW, G->out_sh = W;
+    }
+    if (gout) {
+      q.grad_out[g] = gout[g];
+      q.go_sn[g] = C[g] * HW, q.go_st[g] = 0, q.go_sc[g] = HW, q.go_sh[g] = W;
+      float* gs[2] = {gsrc0 ? gsrc0[g] : NULL, gsrc1 ? gsrc1[g] : NULL};
+      for (int d = 0; d < 2; ++d) {
+        q.grad_src[g][d] = gs[d];
+        q.gs_sn[g][d] = C[g] * HW, q.gs_st[g][d] = C[g] * HW /* T = 1: never stepped */,
+        q.gs_sc[g][d] = HW, q.gs_sh[g][d] = W;
+      }
+    }
+  }
+  int rc = 0;
+  if (out) rc = fwo_warp_blend_forward(&p);
+  if (!rc && gout) rc = fwo_warp_blend_backward(&p, &q);
+  return rc;
+}

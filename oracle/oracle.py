@@ -41,6 +41,9 @@ def load() -> C.CDLL:
         lib.fwo_set_num_threads.argtypes = [C.c_int32]
         lib.fwo_base_coord.argtypes = [C.c_int, C.c_int]
         lib.fwo_base_coord.restype = C.c_float
+        fpp = C.POINTER(C.c_void_p)
+        lib.fwo_bidir_contig.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32), fpp, fpp, vp, vp, vp, vp, C.c_int32, C.c_int32,
+                                                           fpp, fpp, fpp, fpp, vp, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -209,3 +212,43 @@ def mask_blend_backward(inp, mask, noise_bg, grad_out):
     gm = (g * (inp - noise[:, None])).sum(axis=2)
     gn = (g * (1.0 - mask[:, :, None])).sum(axis=1)[:, :Cn]
     return gi, gm, gn
+
+
+# ---------------------------------------------------------------------------------------------
+# Flat entry (full-size parity tests): contiguous arrays in, the problem description packed in C by
+# fwo_bidir_contig — independent of the product's _problem.fill_problem.
+# ---------------------------------------------------------------------------------------------
+def bidir_contig(src0, src1, flow0, flow1, blend0=None, blend1=None, grad_outs=None, padding_mode="border", align_corners=False,
+                 want_forward=True):
+    """Bidirectional warp + mask-weighted blend (nets/OpticalUnet.py:123-146) on contiguous fp32 numpy arrays.
+
+    src0[g], src1[g] [N,C,H,W]; flow0, flow1 [N,2,H,W]; blend0, blend1 [N,H,W] (or [N,1,H,W]) or None; grad_outs[g] [N,C,H,W].
+    Returns dict(out=[...], gsrc0=[...], gsrc1=[...], gflow0, gflow1, gblend0, gblend1) (absent parts are None)."""
+    c32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    src0, src1 = [c32(a) for a in src0], [c32(a) for a in src1]
+    flow0, flow1, blend0, blend1 = c32(flow0), c32(flow1), c32(blend0), c32(blend1)
+    N, _, H, W = flow0.shape
+    G = len(src0)
+    Cs = (C.c_int32 * G)(*[a.shape[1] for a in src0])
+    arr = lambda xs: None if xs is None else (C.c_void_p * G)(*[x.ctypes.data for x in xs])
+    out = [np.empty_like(a) for a in src0] if want_forward else None
+    res = dict(out=out, gsrc0=None, gsrc1=None, gflow0=None, gflow1=None, gblend0=None, gblend1=None)
+    gos = None
+    if grad_outs is not None:
+        gos = [c32(g) for g in grad_outs]
+        res["gsrc0"], res["gsrc1"] = [np.zeros_like(a) for a in src0], [np.zeros_like(a) for a in src1]
+        res["gflow0"], res["gflow1"] = np.zeros_like(flow0), np.zeros_like(flow1)
+        if blend0 is not None:
+            res["gblend0"] = np.zeros((N, H, W), np.float32)
+        if blend1 is not None:
+            res["gblend1"] = np.zeros((N, H, W), np.float32)
+    p = lambda a: None if a is None else a.ctypes.data
+    rc = load().fwo_bidir_contig(N, H, W, G, Cs, arr(src0), arr(src1), p(flow0), p(flow1), p(blend0), p(blend1), _PAD[padding_mode],
+                                 int(bool(align_corners)), arr(out), arr(gos), arr(res["gsrc0"]), arr(res["gsrc1"]), p(res["gflow0"]),
+                                 p(res["gflow1"]), p(res["gblend0"]), p(res["gblend1"]))
+    if rc:
+        raise ValueError(f"oracle bidir_contig: code {rc}")
+    return res
+
+
+_PAD = {"zeros": 0, "border": 1}  # FWB_PAD_ZEROS / FWB_PAD_BORDER (include/flowwarp_b200.h)

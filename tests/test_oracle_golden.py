@@ -123,3 +123,33 @@ def test_refine_blend_golden(oracle, golden_dir, name):
     assert relerr(gi, z["grad_input"]) <= BWD_TOL
     assert relerr(gm, z["grad_mask"]) <= BWD_TOL
     assert relerr(gn, z["grad_noise"]) <= BWD_TOL
+
+
+@pytest.mark.parametrize("pad,align", [("border", False), ("zeros", True)])
+def test_flat_entry_matches_struct_entry_and_torch(oracle, pad, align):
+    """fwo_bidir_contig (problem packed in C from shapes: the full-size GPU tests' checker) == the struct-packed oracle entry
+    bit for bit, and == the torch restatement of nets/OpticalUnet.py:123-146 within the parity bars."""
+    N, H, W = 2, 40, 56
+    f0 = [synth.rgb(0, N, H, W, 3), synth.seg(1, N, H, W, 5)]
+    f1 = [synth.rgb(10, N, H, W, 3), synth.seg(11, N, H, W, 5)]
+    ff, fb = synth.flow(3, N, H, W, 6.0), synth.flow(4, N, H, W, 6.0)
+    mf, mb = synth.mask(2, N, H, W), synth.mask(12, N, H, W)
+    gos = [synth.grad(5 + i, a.shape) for i, a in enumerate(f0)]
+    flat = oracle.bidir_contig(f0, f1, ff, fb, mf[:, 0], mb[:, 0], grad_outs=gos, padding_mode=pad, align_corners=align)
+    ref = oracle.forward(list(zip(f0, f1)), [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode=pad, align_corners=align)
+    for g in range(2):
+        assert np.array_equal(flat["out"][g], ref[g][:, 0])
+        assert np.array_equal(flat["gsrc0"][g], rg["grad_srcs"][g][0][:, 0])
+        assert np.array_equal(flat["gsrc1"][g], rg["grad_srcs"][g][1][:, 0])
+    assert np.array_equal(flat["gflow0"], rg["grad_flows"][0][:, :, 0]) and np.array_equal(flat["gflow1"], rg["grad_flows"][1][:, :, 0])
+    assert np.array_equal(flat["gblend0"], rg["grad_blends"][0][:, 0]) and np.array_equal(flat["gblend1"], rg["grad_blends"][1][:, 0])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).requires_grad_()
+    a0, a1 = [t(a) for a in f0], [t(a) for a in f1]
+    tff, tfb, tmf, tmb = t(ff), t(fb), t(mf), t(mb)
+    outs = torch_ref.ref_warp_blend(a0, a1, tff, tfb, tmf, tmb, padding_mode=pad, align_corners=align)
+    torch.autograd.backward(outs, [torch.from_numpy(g) for g in gos])
+    for g in range(2):
+        assert relerr(flat["out"][g], outs[g].detach().numpy()) <= 1e-6
+        assert relerr(flat["gsrc0"][g], a0[g].grad.numpy()) <= 1e-5 and relerr(flat["gsrc1"][g], a1[g].grad.numpy()) <= 1e-5
+    assert relerr(flat["gflow0"], tff.grad.numpy()) <= 1e-5 and relerr(flat["gblend1"], tmb.grad.numpy()[:, 0]) <= 1e-5
