@@ -104,6 +104,7 @@ SYMBOLS = (
     "fwb_version",
     "fwb_strerror",
     "fwb_reload_env",
+    "fwb_release_cache",
     "fwb_warp_blend_forward",
     "fwb_warp_blend_forward_zero",
     "fwb_label_warp_blend_forward",
@@ -139,6 +140,8 @@ def load() -> C.CDLL:
     lib.fwb_version.argtypes = []
     lib.fwb_reload_env.restype = None
     lib.fwb_reload_env.argtypes = []
+    lib.fwb_release_cache.restype = None
+    lib.fwb_release_cache.argtypes = []
     lib.fwb_strerror.restype = C.c_char_p
     lib.fwb_strerror.argtypes = [C.c_int32]
     lib.fwb_warp_blend_forward.restype = C.c_int32

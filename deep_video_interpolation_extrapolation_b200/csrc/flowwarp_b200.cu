@@ -287,15 +287,16 @@ static dim3 pixel_grid(const fwb_problem* p) {
 }
 
 // Kernel selection.  Defaults are the fastest measured variants:
-//   forward            shared-memory tile kernel (fwb_tile.cuh)              ("notile" / "generic": one-thread-per-pixel gather)
+//   forward            texture-gather kernel (fwb_tex.cuh) on dense sources  ("notex": shared-memory tile kernel, fwb_tile.cuh;
+//                                                                             "notile" / "generic": one-thread-per-pixel LDG gather)
 //   backward, fast     kernels 2+3 fused on tiles, shared accumulators + RED  ("nofuse": split kernels, atomics-free)
 //   backward, determ.  generic kernel 2 + owner-gather kernel 3
 // FWB_KERNELS=<comma separated words> and the FWB_TILE_* sizes switch variants for A/B measurements and for the tests that
 // keep every variant parity-checked.  The environment is read ONCE per process (thread-safe); fwb_reload_env() re-reads it.
-enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u };
+enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u, KN_NOTEX = 256u };
 struct EnvCfg {
   unsigned knobs;
-  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwd_ppt;
+  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwdx_kb, tile_bwd_ppt;
 };
 static EnvCfg g_env;
 static std::atomic<int> g_env_ready{0};
@@ -313,11 +314,13 @@ static void env_load_locked() {
     if (strstr(v, "generic")) e.knobs |= KN_GENERIC;
     if (strstr(v, "notile")) e.knobs |= KN_NOTILE;
     if (strstr(v, "nozfuse")) e.knobs |= KN_NOZFUSE;
+    if (strstr(v, "notex")) e.knobs |= KN_NOTEX;
   }
   e.tile_bwd_ppt = env_int("FWB_TILE_BWD_PPT", 2);
   e.tile_fwd_kb = env_int("FWB_TILE_FWD_KB", 52);
   e.tile_bwd_kb = env_int("FWB_TILE_BWD_KB", e.tile_bwd_ppt == 1 ? 48 : 80);
   e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
+  e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 48);
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }
@@ -417,6 +420,119 @@ static int set_smem_ptr(const void* fn, int bytes) {
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   return set_smem_ptr(reinterpret_cast<const void*>(kernel), bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Texture objects over dense source tensors (fwb_tex.cuh).  A texture object is a descriptor (address, extent, pitch): it
+// stays valid for as long as the memory does, so objects are created once per (pointer, extent, pitch, device) and kept in a
+// process-wide, mutex-guarded cache that is never evicted while kernels may be in flight: when it is full the caller simply
+// takes the shared-memory tile path.  fwb_release_cache() destroys the objects (caller guarantees the device is idle).
+// ---------------------------------------------------------------------------------------------
+struct TexEntry {
+  const void* ptr;
+  int width, rows, dev;
+  size_t pitch;
+  cudaTextureObject_t obj;
+};
+struct TexLimits {
+  int dev, maxw, maxh, align, palign;
+};
+static std::mutex g_tex_mu;
+static std::vector<TexEntry> g_tex;
+static std::vector<TexLimits> g_texlim;
+constexpr size_t TEX_CACHE_MAX = 4096;
+
+static bool tex_limits(int dev, TexLimits& L) {  // g_tex_mu held
+  for (const TexLimits& l : g_texlim)
+    if (l.dev == dev) {
+      L = l;
+      return true;
+    }
+  L.dev = dev;
+  if (cudaDeviceGetAttribute(&L.maxw, cudaDevAttrMaxTexture2DLinearWidth, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&L.maxh, cudaDevAttrMaxTexture2DLinearHeight, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&L.align, cudaDevAttrTextureAlignment, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&L.palign, cudaDevAttrTexturePitchAlignment, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  g_texlim.push_back(L);
+  return true;
+}
+
+static bool tex_get(const float* ptr, int width, int rows, size_t pitch, int dev, unsigned long long* out) {  // g_tex_mu held
+  for (const TexEntry& e : g_tex)
+    if (e.ptr == ptr && e.width == width && e.rows == rows && e.pitch == pitch && e.dev == dev) {
+      *out = (unsigned long long)e.obj;
+      return true;
+    }
+  if (g_tex.size() >= TEX_CACHE_MAX) return false;
+  cudaResourceDesc rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypePitch2D;
+  rd.res.pitch2D.devPtr = const_cast<float*>(ptr);
+  rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+  rd.res.pitch2D.width = (size_t)width;
+  rd.res.pitch2D.height = (size_t)rows;
+  rd.res.pitch2D.pitchInBytes = pitch;
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  // creating a descriptor enqueues nothing; allow it while the calling thread is capturing a CUDA graph
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  (void)cudaThreadExchangeStreamCaptureMode(&mode);
+  cudaTextureObject_t obj = 0;
+  const cudaError_t e = cudaCreateTextureObject(&obj, &rd, &td, nullptr);
+  (void)cudaThreadExchangeStreamCaptureMode(&mode);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  g_tex.push_back({ptr, width, rows, dev, pitch, obj});
+  *out = (unsigned long long)obj;
+  return true;
+}
+
+// Can every source of the problem be read through textures?  Fills X (texture objects, block geometry) if so.
+static bool tex_prepare(const fwb_problem* p, TexP& X) {
+  if (knobs() & (KN_NOTEX | KN_GENERIC)) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lk(g_tex_mu);
+  TexLimits L;
+  if (!tex_limits(dev, L) || p->W > L.maxw) return false;
+  memset(&X, 0, sizeof(X));
+  for (int g = 0; g < p->n_groups; ++g)
+    for (int d = 0; d < p->n_dirs; ++d) {
+      const fwb_group& R = p->grp[g];
+      const long long sh = R.src_sh[d], sc = R.src_sc[d], st = R.src_st[d], sn = R.src_sn[d], C = R.C;
+      const int Tn = (p->T == 1 || st == 0) ? 1 : p->T;
+      if (sh < p->W || (sh * 4) % L.palign || sc != (long long)p->H * sh) return false;
+      if (Tn > 1 && st != C * sc) return false;
+      if (p->N > 1 && sn != Tn * C * sc) return false;
+      const long long rows_n = (long long)Tn * C * p->H;
+      if (rows_n > L.maxh || rows_n > (1 << 23)) return false;
+      if ((uintptr_t)R.src[d] % (uintptr_t)L.align) return false;
+      long long nb = L.maxh / rows_n;
+      if (nb > p->N) nb = p->N;
+      if (nb > 1024) nb = 1024;
+      while (nb > 1 && ((nb * sn * 4) % L.align)) --nb;  // every block of clips must start on a texture-aligned address
+      if (nb < p->N && ((nb * sn * 4) % L.align)) return false;
+      const long long nblk = (p->N + nb - 1) / nb;
+      if (nblk > TX_MAXBLK) return false;
+      TexSrc& S = X.s[g][d];
+      S.nb = (int)nb;
+      S.rows_n = (int)rows_n;
+      S.rows_t = Tn > 1 ? (int)(C * p->H) : 0;
+      for (long long b = 0; b < nblk; ++b) {
+        const long long n0 = b * nb, cnt = (p->N - n0 < nb) ? p->N - n0 : nb;
+        if (!tex_get(R.src[d] + n0 * sn, p->W, (int)(cnt * rows_n), (size_t)sh * 4, dev, &S.tex[b])) return false;
+      }
+    }
+  return true;
 }
 
 }  // namespace fwb
@@ -536,6 +652,12 @@ void fwb_reload_env(void) {
   env_load_locked();
 }
 
+void fwb_release_cache(void) {
+  std::lock_guard<std::mutex> lk(g_tex_mu);
+  for (const TexEntry& e : g_tex) (void)cudaDestroyTextureObject(e.obj);
+  g_tex.clear();
+}
+
 const char* fwb_strerror(int32_t code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   switch (code) {
@@ -568,12 +690,14 @@ static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stre
   if (zq && (rc = to_grads(p, zq, Q))) return rc;
   if (p->N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tile = !(knobs() & KN_NOTILE) && stage_ok(p) && tile_fwd_ok(p);
+  TexP X;
+  const bool tex = tex_prepare(p, X);
+  const bool tile = !tex && !(knobs() & KN_NOTILE) && stage_ok(p) && tile_fwd_ok(p);
   ZeroP Z;
   memset(&Z, 0, sizeof(Z));
   if (zq) {
     // in-kernel zero-fill needs 16-byte aligned rows and one row stride per direction; anything else: memsets first
-    bool fuse = tile && !(knobs() & KN_NOZFUSE), any = false;
+    bool fuse = (tex || tile) && !(p->W & 3) && !(knobs() & KN_NOZFUSE), any = false;
     int sh[2] = {0, 0};
     for (int g = 0; g < p->n_groups; ++g)
       for (int d = 0; d < p->n_dirs; ++d) {
@@ -592,6 +716,14 @@ static int32_t run_forward(const fwb_problem* p, const fwb_grads* zq, void* stre
     Z.sh[1] = sh[1];
     Z.on = (fuse && any) ? 1 : 0;
     if (any && !Z.on && (rc = zero_grad_src(p, Q, s))) return rc;
+  }
+  if (tex) {
+    const dim3 grid((p->W + TXF_TW - 1) / TXF_TW, (p->H + TXF_TH - 1) / TXF_TH, p->N * p->T);
+    if (p->n_dirs == 2)
+      fwd_tex_kernel<2><<<grid, TXF_THREADS, 0, s>>>(P, X, Z, total_channels(p));
+    else
+      fwd_tex_kernel<1><<<grid, TXF_THREADS, 0, s>>>(P, X, Z, total_channels(p));
+    return (int32_t)cudaGetLastError();
   }
   if (tile) {
     const int sb = env().tile_fwd_kb * 1024;
@@ -801,20 +933,31 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
       if (any_gs && !(p->flags & FWB_FLAG_GRAD_SRC_ZEROED) && (rc = zero_grad_src(p, Q, s))) return rc;
       if (tile_ok) {
         const int ppt = env().tile_bwd_ppt;  // pixels per thread: 1 = 32x8 tiles, 3 CTAs/SM; 2 = 32x16 tiles, 2 CTAs/SM
+        TexP X;
+        const bool tex = ppt != 1 && tex_prepare(p, X);
+        if (!tex) memset(&X, 0, sizeof(X));
         const int sb = env().tile_bwd_kb * 1024;
         const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);
 #define FWB_LAUNCH_TBWD(D, A, B)                                                                  \
   do {                                                                                            \
     if (ppt == 1) {                                                                               \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 1, 2>, sb))) return rc;                         \
-      bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
+      bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4, X);               \
+    } else if (!any_src && tex) { /* flow-only backward on the texture path: no shared-memory stages at all */ \
+      const int sbx = 16 * 1024;                                                                  \
+      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false, true>, sbx))) return rc; \
+      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false, true><<<grid, TL_THREADS, sbx, s>>>(P, Q, sbx / 4, X); \
     } else if (!any_src) { /* flow-only backward: no accumulators, 3 CTAs/SM */                   \
-      const int sbn = env().tile_bwdf_kb * 1024;                                     \
+      const int sbn = env().tile_bwdf_kb * 1024;                                                  \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false>, sbn))) return rc;     \
-      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false><<<grid, TL_THREADS, sbn, s>>>(P, Q, sbn / 4); \
+      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false><<<grid, TL_THREADS, sbn, s>>>(P, Q, sbn / 4, X); \
+    } else if (tex) { /* texture gather + shared-memory scatter: shared memory holds the two accumulators only */ \
+      const int sbx = env().tile_bwdx_kb * 1024;                                                  \
+      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, true, true>, sbx))) return rc; \
+      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, true, true><<<grid, TL_THREADS, sbx, s>>>(P, Q, sbx / 4, X); \
     } else {                                                                                      \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3>, sb))) return rc;                         \
-      bwd_tile_kernel<D, A, B, 2, 3><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4);                  \
+      bwd_tile_kernel<D, A, B, 2, 3><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4, X);               \
     }                                                                                             \
   } while (0)
         const int key = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);

@@ -55,6 +55,7 @@ __device__ __forceinline__ float* zero_plane(const ZeroP& Z, const Geo& G, int g
 }
 
 constexpr int TXF_THREADS = 256;
+constexpr int TXF_CB = 4;  // channels per batch of texture fetches
 constexpr int TXF_TW = 32, TXF_TH = 8;  // CTA tile: 4 x 2 warp patches of 8 x 4 pixels
 
 // ---------------------------------------------------------------------------------------------
@@ -108,22 +109,32 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
     }
     float* out = R.out + n * R.out_sn + t * R.out_st + (long long)i * R.out_sh + j;
     const float fH = (float)G.H;
-#pragma unroll 4
-    for (int c = 0; c < R.C; ++c) {
-      float r = 0.0f;
+    // channels in batches of TXF_CB: all texture fetches of a batch are issued before the first result is used
+    for (int c0 = 0; c0 < R.C; c0 += TXF_CB) {
+      float4 q[TXF_CB][NDIRS];
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        float a, b, cc, dd;
-        tex_quad(tx[d], fx1[d], row[d], v[d], a, b, cc, dd);
-        row[d] += fH;  // next plane of the slab (integers below 2^24: exact)
-        float s = __fmul_rn(a, w[d][0]);
-        s = __fmaf_rn(b, w[d][1], s);
-        s = __fmaf_rn(cc, w[d][2], s);
-        s = __fmaf_rn(dd, w[d][3], s);
-        if (has_bl[d]) s = __fmul_rn(s, bl[d]);
-        r = (d == 0) ? s : __fadd_rn(r, s);
+      for (int u = 0; u < TXF_CB; ++u)
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d)  // rows past the last channel stay inside the slab or clamp: fetched, never used
+          q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)tx[d], fx1[d], row[d] + (float)u * fH, 0);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) row[d] += (float)TXF_CB * fH;  // integers below 2^24: exact
+#pragma unroll
+      for (int u = 0; u < TXF_CB; ++u) {
+        float r = 0.0f;
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          const float a = (v[d] & 1u) ? q[u][d].w : 0.0f, b = (v[d] & 2u) ? q[u][d].z : 0.0f;
+          const float cc = (v[d] & 4u) ? q[u][d].x : 0.0f, dd = (v[d] & 8u) ? q[u][d].y : 0.0f;
+          float s = __fmul_rn(a, w[d][0]);
+          s = __fmaf_rn(b, w[d][1], s);
+          s = __fmaf_rn(cc, w[d][2], s);
+          s = __fmaf_rn(dd, w[d][3], s);
+          if (has_bl[d]) s = __fmul_rn(s, bl[d]);
+          r = (d == 0) ? s : __fadd_rn(r, s);
+        }
+        if (in && c0 + u < R.C) __stcs(out + (long long)(c0 + u) * R.out_sc, r);
       }
-      if (in) __stcs(out + (long long)c * R.out_sc, r);
     }
   }
   if (Z.on) {  // 64 float4 per plane and tile: a quarter of the CTA per plane, planes round robin

@@ -44,6 +44,9 @@ constexpr bool TL_FILL_GAPS = false;           // A/B: fill the row placement ga
 #ifndef TL_BWD_MINCTA
 #define TL_BWD_MINCTA 2  // resident CTAs per SM the scatter backward is compiled for (3 = 85 registers: measured below)
 #endif
+#ifndef TL_BWDX_MINCTA
+#define TL_BWDX_MINCTA 2  // resident CTAs per SM the texture-path scatter backward is compiled for
+#endif
 #ifndef TL_SMOOTH_LEN4
 #define TL_SMOOTH_LEN4 10  // a tile whose widest row segment has at most this many 16-byte pieces counts as near-rigid
 #endif
@@ -54,6 +57,8 @@ struct TilePix {  // per (pixel of this thread, direction)
   float tx, ty, ux, uy, bl;
   unsigned clip;  // bit 0 / 1: border padding clipped ix / iy (the coordinate gradient is then zero)
   int o0, o1;  // float offsets inside a stage of the nw and sw taps
+  float fx1, fy1;  // x0 + 1, y0 + 1 (texture path: fwb_tex.cuh); 0 when the pixel has no tap in this tile
+  unsigned vld;    // validity bits of the 4 taps (0 for slow / out-of-image pixels)
 };
 
 // Row-segment table of one direction.  Row r is source row ybase + r.  The segment of row r, 4-aligned columns
@@ -346,6 +351,9 @@ __device__ __forceinline__ void tile_prologue(const Params& P, TileTab* tb, Stag
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       cx.px[q][d].o0 = cx.px[q][d].o1 = 0;
+      cx.px[q][d].vld = vld[q][d];
+      cx.px[q][d].fx1 = vld[q][d] ? (float)(x0[q][d] + 1) : 0.0f;
+      cx.px[q][d].fy1 = vld[q][d] ? (float)(y0[q][d] + 1) : 0.0f;
       if (vld[q][d]) {
         const int r = y0[q][d] - yb;
         cx.px[q][d].o0 = doff + T.rowbase[r] + (x0[q][d] - T.rowx[r]);
@@ -612,6 +620,9 @@ struct TileChanB {
   float* gs[2];  // may be NULL
   const float* go;
   int g, c;  // group / channel (the non-finite path needs them)
+  unsigned long long tex[2];  // texture path: object holding this channel's plane, per direction
+  float row[2];               //               first texture row of the plane
+  int pad_[2];
 };
 
 // inf / NaN in grad_out of this channel: exact float atomics straight to global memory (rare path, kept out of line)
@@ -623,9 +634,13 @@ __device__ __noinline__ void bwd_nonfinite_px(const Params& P, const GradP& Q, i
 
 // SCATTER = false: no grad_src is wanted (the sources are data): kernel 2 only on the staged tiles - no accumulators, no scale
 // vote, no flush; fewer registers and 4 instead of 6 shared-memory units per CTA, hence 3 CTAs per SM.
-template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS, bool SCATTER = true>
-__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER) ? 3 : TL_BWD_MINCTA)) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
-                                                                 int smem_floats) {
+// TEX = true: the source taps come from the texture units (fwb_tex.cuh: one TLD4 per (pixel, direction, channel), fetched one
+// channel ahead) instead of a staged copy of the footprint; shared memory then only holds the two scatter accumulators and the
+// shared-memory pipe only carries the scatter.  The two pipes run side by side (tools/mb_tex.cu: TLD4 alone 18.5, 4 ATOMS alone
+// 19.0, both together 20.5 cycles per warp, direction and channel).
+template <int NDIRS, bool ALIGN, bool BORDER, int PPT, int SLOTS, int NTHR = TL_THREADS, bool SCATTER = true, bool TEX = false>
+__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER) ? 3 : (TEX ? TL_BWDX_MINCTA : TL_BWD_MINCTA))) bwd_tile_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+                                                                 int smem_floats, const __grid_constant__ TexP X) {
   extern __shared__ float4 tl_smem4[];
   float* const smem = reinterpret_cast<float*>(tl_smem4);
   __shared__ StageSlow slow;
@@ -644,6 +659,8 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
   unsigned info[SLOTS];
   unsigned pd[SLOTS];  // byte offset inside a stage of piece tid + s*256
   unsigned clipbits = 0u;  // 2 bits per (q, d): the coordinate gradient is zero (border clipping)
+  float fx1[PPT][NDIRS], fy1[PPT][NDIRS];  // texture path: quad coordinates
+  unsigned vbits = 0u;                      //               4 validity bits per (q, d)
   // grad_out of the first channel: issued before the prologue so that its latency hides behind it (the scale vote of
   // channel 0 is the first thing the pipeline needs)
   float ego[PPT];
@@ -662,7 +679,8 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
   }
   {
     TileCtx<NDIRS, PPT, SLOTS> cx;
-    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS, NTHR>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats, SCATTER ? TL_BD + 2 : TL_BD, cx);
+    tile_prologue<NDIRS, ALIGN, BORDER, PPT, SLOTS, NTHR>(P, reinterpret_cast<TileTab*>(smem), slow, slowtap, smem_floats,
+                                                          (TEX ? 0 : TL_BD) + (SCATTER ? 2 : 0), cx);
     n = cx.n, t = cx.t, j = cx.j;
     if (!cx.ok) {
 #pragma unroll
@@ -683,6 +701,8 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
         clipbits |= px.clip << (2 * (q * NDIRS + d));
         a0[q][d] = 4u * (unsigned)px.o0;
         a1[q][d] = 4u * (unsigned)px.o1;
+        fx1[q][d] = px.fx1, fy1[q][d] = px.fy1;
+        vbits |= px.vld << (4 * (q * NDIRS + d));
       }
     }
 #pragma unroll
@@ -705,6 +725,14 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
           e.src[d] = R.src[d] + n * R.src_sn[d] + t * R.src_st[d] + (long long)c * R.src_sc[d];
           float* gs = (d < NDIRS) ? Q.grad_src[g][d] : nullptr;
           e.gs[d] = gs ? gs + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)c * Q.gs_sc[g][d] : nullptr;
+          e.tex[d] = 0ull;
+          e.row[d] = 0.0f;
+          if (TEX && d < NDIRS) {
+            const TexSrc& S = X.s[g][d];
+            const int blk = n / S.nb;
+            e.tex[d] = S.tex[blk];
+            e.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t + c * G.H);
+          }
         }
         e.go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)c * Q.go_sc[g];
         e.g = g;
@@ -754,17 +782,27 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
   for (int q = 0; q < PPT; ++q) gooff[q] = irow[q] * Q.go_sh[g0] + j;
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned stage_b = 4u * (unsigned)stage_f;
-  const unsigned acc_s = smem_s + TL_BD * stage_b;  // two accumulators, stage layout
+  const unsigned acc_s = smem_s + (TEX ? 0u : TL_BD * stage_b);  // two accumulators, stage layout
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s)
     if (goff[s] >= 0) {  // the pieces this thread flushes start from zero (the rest of the accumulators is never read)
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + pd[s]), "r"(0) : "memory");
       asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + stage_b + pd[s]), "r"(0) : "memory");
     }
-  if (threadIdx.x < TL_BD * TL_ZPAD) smem[(threadIdx.x / TL_ZPAD) * stage_f + (threadIdx.x % TL_ZPAD)] = 0.f;
+  if (!TEX && threadIdx.x < TL_BD * TL_ZPAD) smem[(threadIdx.x / TL_ZPAD) * stage_f + (threadIdx.x % TL_ZPAD)] = 0.f;
   const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
 
+  float4 qc[PPT][NDIRS], qn[PPT][NDIRS];  // texture path: the quads of channel cf / cf + 1
+  auto fetch = [&](int cf, float4 (*q)[NDIRS]) {
+    const TileChanB& tc = tab[cf < Cn ? cf : 0];
+#pragma unroll
+    for (int qq = 0; qq < PPT; ++qq)
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d)
+        q[qq][d] = tex2Dgather<float4>((cudaTextureObject_t)tc.tex[d], fx1[qq][d], tc.row[d] + fy1[qq][d], 0);
+  };
   auto issue = [&](int cf, unsigned soff) {
+    if (TEX) return;
     const bool live = cf < Cn;
     const unsigned te = tab_s + (unsigned)sizeof(TileChanB) * (unsigned)(live ? cf : 0);
 #pragma unroll
@@ -809,6 +847,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
 #pragma unroll
     for (int p = 0; p < TL_BD - 1; ++p, so += stage_b) issue(p, so);
   }
+  if (TEX && Cn > 0) fetch(0, qc);
   float go[PPT], gn[PPT];
 #pragma unroll
   for (int q = 0; q < PPT; ++q) go[q] = (Cn > 0 && act[q]) ? ego[q] : 0.f;  // channel 0 (loaded before the prologue)
@@ -858,9 +897,10 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
   bool flush_prev = false;
 #pragma unroll 1
   for (int cf = 0; cf < Cn; ++cf) {
-    cp_async_wait<TL_BD - 2>();
+    if (!TEX) cp_async_wait<TL_BD - 2>();
     __syncthreads();  // channel cf has landed; scatter of cf-1 complete; flush of cf-2 complete
     issue(cf + TL_BD - 1, poffs);
+    if (TEX && cf + 1 < Cn) fetch(cf + 1, qn);  // the quads of the next channel travel while this one is scattered
     load_go(cf + 1, gn);
     if (SCATTER && threadIdx.x == 0) amax_s[(cf + 2) % 3] = 0u;
     if (SCATTER && flush_prev) flush(cf - 1, acc_s + (aoff ^ stage_b), Sinv_prev);
@@ -880,8 +920,15 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
     for (int q = 0; q < PPT; ++q) {
 #pragma unroll
       for (int d = 0; d < NDIRS; ++d) {
-        const float a = tl_lds(sb + a0[q][d]), b = tl_lds4(sb + a0[q][d]);
-        const float c_ = tl_lds(sb + a1[q][d]), dd = tl_lds4(sb + a1[q][d]);
+        float a, b, c_, dd;
+        if (TEX) {  // taps outside the image (and every tap of a slow / out-of-tile pixel) count as zero
+          const unsigned v = vbits >> (4 * (q * NDIRS + d));
+          a = (v & 1u) ? qc[q][d].w : 0.f, b = (v & 2u) ? qc[q][d].z : 0.f;
+          c_ = (v & 4u) ? qc[q][d].x : 0.f, dd = (v & 8u) ? qc[q][d].y : 0.f;
+        } else {
+          a = tl_lds(sb + a0[q][d]), b = tl_lds4(sb + a0[q][d]);
+          c_ = tl_lds(sb + a1[q][d]), dd = tl_lds4(sb + a1[q][d]);
+        }
         float gw = go[q];
         if (has_bl[d]) {
           const float top = fmaf(b, tx[q][d], a * ux[q][d]), bot = fmaf(dd, tx[q][d], c_ * ux[q][d]);
@@ -908,6 +955,12 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 2 : ((PPT == 1 || !SCATTER
     if (SCATTER) vote_amax(gn, (cf + 1) % 3);
 #pragma unroll
     for (int q = 0; q < PPT; ++q) go[q] = gn[q];
+    if (TEX) {
+#pragma unroll
+      for (int q = 0; q < PPT; ++q)
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) qc[q][d] = qn[q][d];
+    }
     Sinv_prev = Sinv;
     flush_prev = finite && ab != 0u;
     soff += stage_b;

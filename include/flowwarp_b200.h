@@ -21,9 +21,10 @@
  *   - logical batch is (N, T): T = opt.vid_length frames that share one launch.  A tensor that is
  *     shared by all T frames (the single source frame of warp()) passes a T-stride of 0.
  *   - every function launches asynchronously on `stream` (a cudaStream_t passed as void*), allocates
- *     nothing, never throws and never aborts.  Process-wide state is limited to two caches, both mutex-guarded: the A/B
- *     environment knobs (FWB_KERNELS, FWB_TILE_*: read once, fwb_reload_env() re-reads) and the per-(kernel, device)
- *     record of the dynamic shared-memory attribute already requested from the CUDA runtime.
+ *     no device memory, never throws and never aborts.  Process-wide state is limited to three mutex-guarded caches: the A/B
+ *     environment knobs (FWB_KERNELS, FWB_TILE_*: read once, fwb_reload_env() re-reads), the per-(kernel, device) record
+ *     of the dynamic shared-memory attribute already requested from the CUDA runtime, and the texture-object descriptors
+ *     of dense source tensors (fwb_release_cache() destroys them).
  *   - limits: N*T <= 65535 (grid.z), H, W <= 32767, every in-plane offset (C*channel stride + (H+2)*row stride) < 2^31
  *     for sources, outputs and gradients; violations return FWB_E_SHAPE / FWB_E_RANGE.
  *   - return value: 0 = ok; > 0 = a cudaError_t from a launch; < 0 = FWB_E_* argument error.
@@ -188,6 +189,10 @@ const char* fwb_strerror(int32_t code);
 /* Re-read the A/B environment knobs (FWB_KERNELS, FWB_TILE_*).  They are otherwise read once per process.  Test / A-B hook:
  * do not call it while another thread is inside a launch function. */
 void fwb_reload_env(void);
+
+/* Destroy the cached texture objects (the forward / backward read dense sources through the texture units; the descriptors
+ * are created once per (pointer, extent, pitch, device) and kept).  Call only when no kernel of this library is in flight. */
+void fwb_release_cache(void);
 
 /* Kernel 1 — fused forward: flow->coordinate, floor/fraction, validity, 4-tap bilinear gather
  * over every channel of every group, for 1 or 2 directions, and the blend-weighted sum.

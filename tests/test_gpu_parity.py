@@ -315,7 +315,7 @@ def test_deterministic_mode_bit_exact_run_to_run(pkg):
 
 
 # ---------------------------------------------------------------- every kernel variant stays parity-checked
-VARIANTS = ["", "notile", "generic,nofuse", "nofuse"]
+VARIANTS = ["", "notex", "notile", "notex,notile", "generic,nofuse", "nofuse"]
 
 
 @pytest.mark.parametrize("det", [False, True])
@@ -381,13 +381,14 @@ def test_kernel_variants_deterministic_bit_exact(pkg, monkeypatch, variant):
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("env", [{}, {"FWB_TILE_BWD_PPT": "1"}, {"FWB_TILE_FWD_KB": "8", "FWB_TILE_BWD_KB": "12"}])
+@pytest.mark.parametrize("env", [{}, {"FWB_KERNELS": "notex"}, {"FWB_TILE_BWD_PPT": "1"}, {"FWB_TILE_BWDX_KB": "4"},
+                                 {"FWB_KERNELS": "notex", "FWB_TILE_FWD_KB": "8", "FWB_TILE_BWD_KB": "12"}])
 @pytest.mark.parametrize("pad", ["border", "zeros"])
 @pytest.mark.parametrize("shape", [(2, 37, 52), (1, 16, 32), (1, 130, 260)])
 def test_tile_kernels_ragged_shapes_and_fallbacks(pkg, oracle, monkeypatch, shape, pad, env):
-    """The default (shared-memory tile) kernels on shapes that are not multiples of the 32x16 tile, with 5 % of the
-    pixels thrown out of the image (slow pixels / tap-less pixels), in the 32x8 backward variant, and with a shared
-    memory budget so small that every tile takes the in-kernel generic path."""
+    """The default (texture gather + shared-memory scatter) and the shared-memory tile kernels on shapes that are not
+    multiples of the tile, with 5 % of the pixels thrown out of the image (slow pixels / tap-less pixels), in the 32x8
+    backward variant, and with a shared memory budget so small that every tile takes the in-kernel generic path."""
     _setenv(monkeypatch, **env)
     N, H, W = shape
     f0 = [synth.rgb(0, N, H, W), synth.seg(1, N, H, W, 5)]

@@ -14,7 +14,8 @@ constexpr int N = 16, C = 23, H = 256, W = 512;
 struct Tex { cudaTextureObject_t t[2][N]; };
 
 // MODE 0: tex2Dgather; MODE 1: 4 x tex2D point fetch; MODE 2: 4 x __ldg (generic kernel's way); MODE 3: hybrid, channels
-// below NLDG through __ldg (LSU pipe), the rest through tex2Dgather (TEX pipe)
+// below NLDG through __ldg (LSU pipe), the rest through tex2Dgather (TEX pipe); MODE 4: tex2Dgather + 4 shared-memory integer
+// atomics per (direction, channel) (the backward's scatter), MODE 5: the atomics alone, MODE 6: tex2Dgather + 4 LDS
 template <int MODE, int PW, int NLDG = 0>
 __global__ void __launch_bounds__(256) fwd(const __grid_constant__ Tex T, const float* __restrict__ src0, const float* __restrict__ src1,
                                            const float* __restrict__ fx, const float* __restrict__ fy, float* __restrict__ out) {
@@ -37,13 +38,23 @@ __global__ void __launch_bounds__(256) fwd(const __grid_constant__ Tex T, const 
     w[d][0] = (1 - tx) * (1 - ty), w[d][1] = tx * (1 - ty), w[d][2] = (1 - tx) * ty, w[d][3] = tx * ty;
   }
   float* o = out + ((size_t)n * C * H + i) * W + j;
+  __shared__ int acc[2][2048];
+  unsigned sa[2];
+  if (MODE >= 4) {
+    for (int k = threadIdx.x; k < 4096; k += 256) (&acc[0][0])[k] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < 2; ++d) sa[d] = (unsigned)__cvta_generic_to_shared(&acc[d][(((int)Y[d] & 31) * 44 + ((int)X[d] & 31)) & 2047]);
+  }
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float r = 0.f;
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
       float a, b, cc, dd;
-      if (MODE == 0 || (MODE == 3 && c >= NLDG)) {
+      if (MODE == 5) {
+        a = b = cc = dd = w[d][0];
+      } else if (MODE == 0 || MODE == 4 || MODE == 6 || (MODE == 3 && c >= NLDG)) {
         const float4 q = tex2Dgather<float4>(T.t[d][n], X[d] + 1.0f, Y[d] + 1.0f + (float)(c * H), 0);
         a = q.w, b = q.z, cc = q.x, dd = q.y;  // (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1)
       } else if (MODE == 1) {
@@ -56,6 +67,21 @@ __global__ void __launch_bounds__(256) fwd(const __grid_constant__ Tex T, const 
         a = __ldg(s), b = xi ? __ldg(s + 1) : 0.f, cc = yi ? __ldg(s + W) : 0.f, dd = (xi && yi) ? __ldg(s + W + 1) : 0.f;
       }
       r += a * w[d][0] + b * w[d][1] + cc * w[d][2] + dd * w[d][3];
+      if (MODE == 4 || MODE == 5) {
+        const unsigned ad = sa[d] + (c & 1) * 0;
+        asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(ad), "r"(__float_as_int(a * w[d][0] + 12582912.f)) : "memory");
+        asm volatile("red.shared.add.s32 [%0+4], %1;" ::"r"(ad), "r"(__float_as_int(b * w[d][1] + 12582912.f)) : "memory");
+        asm volatile("red.shared.add.s32 [%0+176], %1;" ::"r"(ad), "r"(__float_as_int(cc * w[d][2] + 12582912.f)) : "memory");
+        asm volatile("red.shared.add.s32 [%0+180], %1;" ::"r"(ad), "r"(__float_as_int(dd * w[d][3] + 12582912.f)) : "memory");
+      }
+      if (MODE == 6) {
+        float l0, l1, l2, l3;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sa[d]));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(l1) : "r"(sa[d]));
+        asm volatile("ld.shared.f32 %0, [%1+176];" : "=f"(l2) : "r"(sa[d]));
+        asm volatile("ld.shared.f32 %0, [%1+180];" : "=f"(l3) : "r"(sa[d]));
+        r += l0 * a + l1 * b + l2 * cc + l3 * dd;
+      }
     }
     __stcs(o + (size_t)c * H * W, r);
   }
@@ -129,6 +155,9 @@ int main() {
   run(fwd<0, 4>, dim3(W / 16, H / 16, N), "tex2Dgather, 4x8 patch", false);
   run(fwd<0, 32>, dim3(W / 128, H / 2, N), "tex2Dgather, 32x1 patch", false);
   run(fwd<1, 8>, dim3(W / 32, H / 8, N), "tex2D point x4, 8x4 patch", false);
+  run(fwd<4, 8>, dim3(W / 32, H / 8, N), "tld4 + 4 ATOMS", false);
+  run(fwd<5, 8>, dim3(W / 32, H / 8, N), "4 ATOMS alone", false);
+  run(fwd<6, 8>, dim3(W / 32, H / 8, N), "tld4 + 4 LDS", false);
   run(fwd<3, 8, 4>, dim3(W / 32, H / 8, N), "hybrid 4 ldg + 19 tld4", false);
   run(fwd<3, 8, 7>, dim3(W / 32, H / 8, N), "hybrid 7 ldg + 16 tld4", false);
   run(fwd<3, 8, 10>, dim3(W / 32, H / 8, N), "hybrid 10 ldg + 13 tld4", false);
