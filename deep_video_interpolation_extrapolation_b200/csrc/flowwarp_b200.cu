@@ -20,6 +20,7 @@
 #include "fwb_generic.cuh"
 #include "fwb_owner.cuh"
 #include "fwb_tile.cuh"
+#include "fwb_bwdx.cuh"
 #include "fwb_blend.cuh"
 #include "fwb_label.cuh"
 
@@ -289,14 +290,17 @@ static dim3 pixel_grid(const fwb_problem* p) {
 // Kernel selection.  Defaults are the fastest measured variants:
 //   forward            texture-gather kernel (fwb_tex.cuh) on dense sources  ("notex": shared-memory tile kernel, fwb_tile.cuh;
 //                                                                             "notile" / "generic": one-thread-per-pixel LDG gather)
-//   backward, fast     kernels 2+3 fused on tiles, shared accumulators + RED  ("nofuse": split kernels, atomics-free)
+//   backward, fast     kernels 2+3 fused: texture gather + integer-atomic shared-memory scatter on dense sources (fwb_tile.cuh,
+//                      TEX = true); kernel 2 alone on the texture units when no source gradient is wanted (fwb_tex.cuh)
+//                      ("sorted": kernel 2 on textures + kernel 3 as a sorted shared-memory gather, fwb_bwdx.cuh, two launches;
+//                       "notex": staged tiles + integer-atomic scatter; "nofuse": split kernels, atomics-free)
 //   backward, determ.  generic kernel 2 + owner-gather kernel 3
 // FWB_KERNELS=<comma separated words> and the FWB_TILE_* sizes switch variants for A/B measurements and for the tests that
 // keep every variant parity-checked.  The environment is read ONCE per process (thread-safe); fwb_reload_env() re-reads it.
-enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u, KN_NOTEX = 256u };
+enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u, KN_NOTEX = 256u, KN_SORTED = 512u };
 struct EnvCfg {
   unsigned knobs;
-  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwdx_kb, tile_bwd_ppt;
+  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwdx_kb, tile_bwd_ppt, bwdx_ppt;
 };
 static EnvCfg g_env;
 static std::atomic<int> g_env_ready{0};
@@ -315,12 +319,14 @@ static void env_load_locked() {
     if (strstr(v, "notile")) e.knobs |= KN_NOTILE;
     if (strstr(v, "nozfuse")) e.knobs |= KN_NOZFUSE;
     if (strstr(v, "notex")) e.knobs |= KN_NOTEX;
+    if (strstr(v, "sorted")) e.knobs |= KN_SORTED;
   }
   e.tile_bwd_ppt = env_int("FWB_TILE_BWD_PPT", 2);
   e.tile_fwd_kb = env_int("FWB_TILE_FWD_KB", 52);
   e.tile_bwd_kb = env_int("FWB_TILE_BWD_KB", e.tile_bwd_ppt == 1 ? 48 : 80);
   e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
-  e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 48);
+  e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 46);
+  e.bwdx_ppt = env_int("FWB_BWDX_PPT", 2);
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }
@@ -936,6 +942,65 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
         TexP X;
         const bool tex = ppt != 1 && tex_prepare(p, X);
         if (!tex) memset(&X, 0, sizeof(X));
+        if (tex && (!any_src || (knobs() & KN_SORTED))) {
+          // no source gradient wanted (the sources are data: the usual training case): kernel 2 alone, on the texture units.
+          // "sorted" (A/B): kernel 2 on the texture units, then kernel 3 as a sorted shared-memory gather (fwb_bwdx.cuh)
+          int want = 0;
+          for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
+          if (want) {
+            const dim3 g2((p->W + TXF_TW - 1) / TXF_TW, (p->H + TXF_TH - 1) / TXF_TH, p->N * p->T);
+            if (p->n_dirs == 2)
+              bwd_flow_tex_kernel<2><<<g2, TXF_THREADS, 0, s>>>(P, Q, X);
+            else
+              bwd_flow_tex_kernel<1><<<g2, TXF_THREADS, 0, s>>>(P, Q, X);
+            if ((rc = (int32_t)cudaGetLastError())) return rc;
+          }
+          if (any_src) {
+            const int sbx = env().tile_bwdx_kb * 1024;
+            const int xp = env().bwdx_ppt == 1 ? 1 : 2;
+            const dim3 g3((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * xp - 1) / (8 * xp), p->N * p->T);
+#define FWB_LAUNCH_SRT(D, A, B)                                                            \
+  do {                                                                                     \
+    if (xp == 1) {                                                                         \
+      if ((rc = set_smem(bwd_src_sorted_kernel<D, A, B, 1>, sbx))) return rc;              \
+      bwd_src_sorted_kernel<D, A, B, 1><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);        \
+    } else {                                                                               \
+      if ((rc = set_smem(bwd_src_sorted_kernel<D, A, B, 2>, sbx))) return rc;              \
+      bwd_src_sorted_kernel<D, A, B, 2><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);        \
+    }                                                                                      \
+  } while (0)
+            const int key3 = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+            const int mc = env_int("FWB_BX_MINCTA", 2);  // A/B (temporary): occupancy variants of the headline instantiation
+            if (key3 == 5 && mc != 2) {
+              if (xp == 2 && mc == 3) {
+                if ((rc = set_smem(bwd_src_sorted_kernel<2, false, true, 2, 3>, sbx))) return rc;
+                bwd_src_sorted_kernel<2, false, true, 2, 3><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);
+              } else if (xp == 1 && mc == 3) {
+                if ((rc = set_smem(bwd_src_sorted_kernel<2, false, true, 1, 3>, sbx))) return rc;
+                bwd_src_sorted_kernel<2, false, true, 1, 3><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);
+              } else if (xp == 1 && mc == 4) {
+                if ((rc = set_smem(bwd_src_sorted_kernel<2, false, true, 1, 4>, sbx))) return rc;
+                bwd_src_sorted_kernel<2, false, true, 1, 4><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);
+              } else {
+                if ((rc = set_smem(bwd_src_sorted_kernel<2, false, true, 2, 4>, sbx))) return rc;
+                bwd_src_sorted_kernel<2, false, true, 2, 4><<<g3, BX_THREADS, sbx, s>>>(P, Q, sbx / 4);
+              }
+              return (int32_t)cudaGetLastError();
+            }
+            switch (key3) {
+              case 0: FWB_LAUNCH_SRT(1, false, false); break;
+              case 1: FWB_LAUNCH_SRT(1, false, true); break;
+              case 2: FWB_LAUNCH_SRT(1, true, false); break;
+              case 3: FWB_LAUNCH_SRT(1, true, true); break;
+              case 4: FWB_LAUNCH_SRT(2, false, false); break;
+              case 5: FWB_LAUNCH_SRT(2, false, true); break;
+              case 6: FWB_LAUNCH_SRT(2, true, false); break;
+              default: FWB_LAUNCH_SRT(2, true, true); break;
+            }
+#undef FWB_LAUNCH_SRT
+          }
+          return (int32_t)cudaGetLastError();
+        }
         const int sb = env().tile_bwd_kb * 1024;
         const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);
 #define FWB_LAUNCH_TBWD(D, A, B)                                                                  \
@@ -943,15 +1008,11 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
     if (ppt == 1) {                                                                               \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 1, 2>, sb))) return rc;                         \
       bwd_tile_kernel<D, A, B, 1, 2><<<grid, TL_THREADS, sb, s>>>(P, Q, sb / 4, X);               \
-    } else if (!any_src && tex) { /* flow-only backward on the texture path: no shared-memory stages at all */ \
-      const int sbx = 16 * 1024;                                                                  \
-      if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false, true>, sbx))) return rc; \
-      bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false, true><<<grid, TL_THREADS, sbx, s>>>(P, Q, sbx / 4, X); \
     } else if (!any_src) { /* flow-only backward: no accumulators, 3 CTAs/SM */                   \
       const int sbn = env().tile_bwdf_kb * 1024;                                                  \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false>, sbn))) return rc;     \
       bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, false><<<grid, TL_THREADS, sbn, s>>>(P, Q, sbn / 4, X); \
-    } else if (tex) { /* texture gather + shared-memory scatter: shared memory holds the two accumulators only */ \
+    } else if (tex) { /* texture gather + integer-atomic scatter: shared memory holds the two accumulators only */ \
       const int sbx = env().tile_bwdx_kb * 1024;                                                  \
       if ((rc = set_smem(bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, true, true>, sbx))) return rc; \
       bwd_tile_kernel<D, A, B, 2, 3, TL_THREADS, true, true><<<grid, TL_THREADS, sbx, s>>>(P, Q, sbx / 4, X); \

@@ -151,4 +151,98 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kernel 2 on the texture path: coordinate gradient -> grad_flow / grad_gate / grad_blend, one thread per output pixel.
+//   gix = sum_c gw_c * [ uy*(v_ne - v_nw) + ty*(v_se - v_sw) ],  giy = sum_c gw_c * [ ux*(v_sw - v_nw) + tx*(v_se - v_ne) ]
+// (ATen grid_sampler_2d_backward with the common factors pulled out; taps outside the image count as zero), the same
+// arithmetic as bwdflow_generic_pixel.  Channels in batches: every texture fetch and grad_out load of a batch is issued
+// before the first result is used.
+// ---------------------------------------------------------------------------------------------
+template <int NDIRS>
+__global__ void __launch_bounds__(TXF_THREADS, 3) bwd_flow_tex_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+                                                                   const __grid_constant__ TexP X) {
+  const Geo& G = P.geo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * TXF_TW + (warp & 3) * 8 + (lane & 7);
+  const int i = blockIdx.y * TXF_TH + (warp >> 2) * 4 + (lane >> 3);
+  int n, t;
+  if (G.T == 1) {
+    n = blockIdx.z;
+    t = 0;
+  } else {
+    n = blockIdx.z / G.T;
+    t = blockIdx.z - n * G.T;
+  }
+  const bool in = j < G.W && i < G.H;
+  const int ic = min(i, G.H - 1), jc = min(j, G.W - 1);  // ragged tiles: clamped address, stores masked
+  // only what the channel loop needs stays in registers; the gradient multipliers, the raw flow and the gate are recomputed for
+  // the final store (once per pixel)
+  float tx[NDIRS], ty[NDIRS], ux[NDIRS], uy[NDIRS], bl[NDIRS];
+  unsigned vld[NDIRS];
+  float gix[NDIRS], giy[NDIRS], gbl[NDIRS], fx1[NDIRS], fy1[NDIRS];
+  bool has_bl[NDIRS];
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    Tap k;
+    compute_tap(G, P.dir[d], n, t, ic, jc, k);
+    tx[d] = k.tx, ty[d] = k.ty, ux[d] = k.ux, uy[d] = k.uy, bl[d] = k.blend, vld[d] = k.valid;
+    gix[d] = giy[d] = gbl[d] = 0.0f;
+    has_bl[d] = P.dir[d].blend != nullptr;
+    fx1[d] = k.valid ? (float)(k.x0 + 1) : 0.0f;
+    fy1[d] = k.valid ? (float)(k.y0 + 1) : 0.0f;
+  }
+  const float fH = (float)G.H;
+  for (int g = 0; g < G.n_groups; ++g) {
+    const GroupP& R = P.grp[g];
+    if (!Q.grad_out[g]) continue;
+    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
+    unsigned long long th[NDIRS];
+    float row[NDIRS];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      const TexSrc& S = X.s[g][d];
+      const int blk = n / S.nb;
+      th[d] = S.tex[blk];
+      row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+    }
+    for (int c0 = 0; c0 < R.C; c0 += TXF_CB) {
+      float4 q[TXF_CB][NDIRS];
+      float gv[TXF_CB];
+#pragma unroll
+      for (int u = 0; u < TXF_CB; ++u) {
+        gv[u] = (c0 + u < R.C) ? __ldcs(go + (long long)(c0 + u) * Q.go_sc[g]) : 0.0f;  // a channel past the end contributes 0
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d] + (float)u * fH, 0);
+      }
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) row[d] += (float)TXF_CB * fH;
+#pragma unroll
+      for (int u = 0; u < TXF_CB; ++u) {
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          const unsigned v = (c0 + u < R.C) ? vld[d] : 0u;  // (the fetched texels of a channel past the end are not finite-safe)
+          const float a = (v & 1u) ? q[u][d].w : 0.0f, b = (v & 2u) ? q[u][d].z : 0.0f;
+          const float cc = (v & 4u) ? q[u][d].x : 0.0f, dd = (v & 8u) ? q[u][d].y : 0.0f;
+          float gw = gv[u];
+          if (has_bl[d]) {
+            const float top = fmaf(b, tx[d], a * ux[d]), bot = fmaf(dd, tx[d], cc * ux[d]);
+            gbl[d] = fmaf(gv[u], fmaf(bot, ty[d], top * uy[d]), gbl[d]);
+            gw = gv[u] * bl[d];
+          }
+          gix[d] = fmaf(gw, fmaf(ty[d], dd - cc, uy[d] * (b - a)), gix[d]);
+          giy[d] = fmaf(gw, fmaf(tx[d], dd - b, ux[d] * (cc - a)), giy[d]);
+        }
+      }
+    }
+  }
+  if (in) {
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      Tap k;
+      compute_tap(G, P.dir[d], n, t, i, j, k);
+      bwdflow_store(P, Q, d, n, t, i, j, k, gix[d], giy[d], gbl[d]);
+    }
+  }
+}
+
 }  // namespace fwb

@@ -54,10 +54,9 @@ __device__ __forceinline__ void scatter_atomic_px(const GradP& Q, int g, int d, 
   }
 }
 
-// one pixel, all channels of all groups: kernel 2's generic body + global-atomic scatter (tiles that do not fit)
+// one pixel, all channels of all groups: global-atomic scatter into grad_src (tiles that do not fit in shared memory)
 template <int NDIRS>
-__device__ __forceinline__ void bwd_fused_generic_pixel(const Params& P, const GradP& Q, int n, int t, int i, int j) {
-  bwdflow_generic_pixel<NDIRS>(P, Q, n, t, i, j);
+__device__ __forceinline__ void bwd_src_generic_pixel(const Params& P, const GradP& Q, int n, int t, int i, int j) {
   Tap k[NDIRS];
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) compute_tap(P.geo, P.dir[d], n, t, i, j, k[d]);
@@ -70,6 +69,13 @@ __device__ __forceinline__ void bwd_fused_generic_pixel(const Params& P, const G
       for (int d = 0; d < NDIRS; ++d) scatter_atomic_px(Q, g, d, n, t, c, k[d], P.dir[d].blend ? gout * k[d].blend : gout);
     }
   }
+}
+
+// ... preceded by kernel 2's generic body (the fused kernels)
+template <int NDIRS>
+__device__ __forceinline__ void bwd_fused_generic_pixel(const Params& P, const GradP& Q, int n, int t, int i, int j) {
+  bwdflow_generic_pixel<NDIRS>(P, Q, n, t, i, j);
+  bwd_src_generic_pixel<NDIRS>(P, Q, n, t, i, j);
 }
 
 }  // namespace fwb

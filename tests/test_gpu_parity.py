@@ -315,7 +315,7 @@ def test_deterministic_mode_bit_exact_run_to_run(pkg):
 
 
 # ---------------------------------------------------------------- every kernel variant stays parity-checked
-VARIANTS = ["", "notex", "notile", "notex,notile", "generic,nofuse", "nofuse"]
+VARIANTS = ["", "sorted", "notex", "notile", "notex,notile", "generic,nofuse", "nofuse"]
 
 
 @pytest.mark.parametrize("det", [False, True])
