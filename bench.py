@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — warp+blend forward+backward throughput (Gpix/s) and HBM-roofline fraction on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|3|4|5] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one pass of the hot path over one batch of synthetic Cityscapes-shaped clips: the fused
@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (N per GPU, H, W, sigma_px, chained steps, allreduce params)
+    1: dict(name="config1: InterNet flow-warp forward, one 3-frame clip 128x256, batch 1 (the reference's CPU-runnable case)", N=1, H=128,
+            W=256, sigma=8.0, chain=1, allreduce=0, fwd_only=True),
     2: dict(name="config2: InterNet warp+blend fwd+bwd 256x512 batch 16", N=16, H=256, W=512, sigma=8.0, chain=1, allreduce=0),
     3: dict(name="config3: ExtraNet 3-step chained warp 512x1024 batch 8", N=8, H=512, W=1024, sigma=8.0, chain=3, allreduce=0),
     4: dict(name="config4: int_9 full-res 1024x2048 batch 4 per GPU", N=4, H=1024, W=2048, sigma=32.0, chain=1, allreduce=0),
@@ -38,6 +40,15 @@ BYTES_PER_PIX = 32 * C_TOTAL + 72  # bidirectional warp+blend fw
 # per-kernel algorithmic bytes/pixel when the three kernels run as separate launches
 KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48, "backward_src": 12 * C_TOTAL + 24,
                 "backward_fused": 20 * C_TOTAL + 48}
+
+
+def config_dict(cfg, args, world):
+    """The `config` object of the JSON line: identical keys in the b200 and the reference arm."""
+    return {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
+            "flow_sigma_px": cfg["sigma"], "chained_steps": cfg["chain"], "padding_mode": "border", "align_corners": False,
+            "forward_only": bool(cfg.get("fwd_only", False)),
+            "parallelism": f"batch-sharded x{world}, no collective in the op",
+            "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"}
 
 
 def ncu_traffic(kernel, cfg_id):
@@ -147,7 +158,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference_step(inp, pad="border"):
+def cpu_reference_step(inp, pad="border", fwd_only=False):
     """The reference's own composition of torch ops (oracle/torch_ref.py restates utils/net_utils.py:93-114 and
     nets/OpticalUnet.py:123-146), forward + backward, on the host cores."""
     import torch
@@ -155,7 +166,8 @@ def cpu_reference_step(inp, pad="border"):
     leaves = [t.detach().clone().requires_grad_() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]]]
     f0, f1, (ff, fb, mf, mb) = leaves[:2], leaves[2:4], leaves[4:]
     outs = torch_ref.ref_warp_blend(f0, f1, ff, fb, mf, mb, padding_mode=pad, align_corners=False)
-    torch.autograd.backward(outs, inp["gos"])
+    if not fwd_only:
+        torch.autograd.backward(outs, inp["gos"])
     return outs
 
 
@@ -165,12 +177,13 @@ def time_cpu_reference(cfg, n_sample, min_seconds, min_reps, max_reps):
     torch.set_num_threads(cores)
     sub = dict(cfg, N=n_sample)
     inp = make_inputs(sub, "cpu")
-    cpu_reference_step(inp)  # warm-up
+    fo = bool(cfg.get("fwd_only", False))
+    cpu_reference_step(inp, fwd_only=fo)  # warm-up
     times = []
     t_all = time.perf_counter()
     while len(times) < max_reps and (len(times) < min_reps or time.perf_counter() - t_all < min_seconds):
         t = time.perf_counter()
-        cpu_reference_step(inp)
+        cpu_reference_step(inp, fwd_only=fo)
         times.append(time.perf_counter() - t)
     pix = n_sample * cfg["H"] * cfg["W"]
     return pix / statistics.median(times) / 1e9, cores, len(times)
@@ -183,18 +196,19 @@ def run_reference_arm(args, cfg, rank, world):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    fo = bool(cfg.get("fwd_only", False))
     probe = make_inputs(dict(cfg, N=1), "cpu")
-    cpu_reference_step(probe)
+    cpu_reference_step(probe, fwd_only=fo)
     t = time.perf_counter()
-    cpu_reference_step(probe)
+    cpu_reference_step(probe, fwd_only=fo)
     t1 = time.perf_counter() - t
     n_s = int(max(1, min(cfg["N"], 90.0 / max((args.steps + args.warmup) * t1, 1e-9))))
     inp = make_inputs(dict(cfg, N=n_s), "cpu")
     for _ in range(args.warmup):
-        cpu_reference_step(inp)
+        cpu_reference_step(inp, fwd_only=fo)
     t = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(inp)
+        cpu_reference_step(inp, fwd_only=fo)
     el = time.perf_counter() - t
     pix = n_s * cfg["H"] * cfg["W"] * cfg["chain"]
     val = pix * args.steps / el / 1e9
@@ -203,8 +217,10 @@ def run_reference_arm(args, cfg, rank, world):
         "impl": "reference", "metric": "warp+blend fwd+bwd Gpix/s", "value": val, "unit": "Gpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(cfg, args, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample,
+                         "what": "oracle/torch_ref.py: the reference's own torch-op sequence (utils/net_utils.py:93-114, "
+                                 "nets/OpticalUnet.py:123-146) restated; the reference has no installable package (no setup.py)"},
         "e2e": {"value": val, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -328,6 +344,61 @@ class CabiStep:
         self.backward_src()
 
 
+class AutogradStep:
+    """The headline op through the PUBLIC autograd API (warp_blend + torch.autograd.backward): what a trainer calls.  Includes
+    the op's own host cost (struct fill, ctypes, output / gradient allocation by torch's caching allocator)."""
+
+    def __init__(self, inp):
+        import deep_video_interpolation_extrapolation_b200 as P
+        self.P, self.gos = P, inp["gos"]
+        G = len(inp["f0"])
+        self.leaves = [t.detach().clone().requires_grad_() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]]]
+        self.G = G
+
+    def step(self):
+        import torch
+        G, lv = self.G, self.leaves
+        outs = self.P.warp_blend(lv[:G], lv[G:2 * G], lv[2 * G], lv[2 * G + 1], lv[2 * G + 2], lv[2 * G + 3])
+        torch.autograd.backward(outs, self.gos)
+        for t in lv:
+            t.grad = None
+
+
+class ChainStep:
+    """config 3: K chained invocations per training step (runners/ExtraTrainer.py:254-310): step k+1 warps [the newer source
+    frame of step k, prediction k]; the predicted seg is re-one-hotted by argmax (:308-310, no gradient through it), the RGB
+    prediction carries the gradient; ONE backward over the whole chain (every step has its own loss terms, :284-288).
+    Through the public autograd op.  Flows / masks of every step are network outputs (requires_grad); the frames are data."""
+
+    def __init__(self, inp, K, cfg, dev, seed):
+        import deep_video_interpolation_extrapolation_b200 as P
+        self.P, self.K, self.gos = P, K, inp["gos"]
+        self.f0 = [t.detach() for t in inp["f0"]]
+        self.f1 = [t.detach() for t in inp["f1"]]
+        self.nets = []  # per step: ff, fb, mf, mb
+        for k in range(K):
+            src = inp if k == 0 else make_inputs(cfg, dev, seed=seed + 1000 * k)
+            self.nets.append([src[n].detach().clone().requires_grad_() for n in ("ff", "fb", "mf", "mb")])
+            if k:
+                del src
+
+    def step(self):
+        import torch
+        A, B = self.f0, self.f1
+        outs_all = []
+        for k in range(self.K):
+            ff, fb, mf, mb = self.nets[k]
+            o = self.P.warp_blend(A, B, ff, fb, mf, mb)
+            outs_all += o
+            if k + 1 < self.K:
+                lab = o[1].argmax(dim=1, keepdim=True)
+                A, B = B, [o[0], torch.zeros_like(o[1]).scatter_(1, lab, 1.0)]
+        torch.autograd.backward(outs_all, self.gos * self.K)
+        for net in self.nets:
+            for t in net:
+                t.grad = None
+
+
 def timed(fn, steps, warmup, sync):
     import torch
     for _ in range(warmup):
@@ -364,13 +435,24 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     inp = make_inputs(cfg, dev, seed=rank)
     ar_buf = torch.zeros(cfg["allreduce"], device=dev) if cfg["allreduce"] else None
     chain = cfg["chain"]
-    step = CabiStep(inp, args.deterministic, atomic_src=args.atomic_src, zero=args.zero)
+    fwd_only = bool(cfg.get("fwd_only", False))
+    step = CabiStep(inp, args.deterministic, atomic_src=args.atomic_src, zero="memset" if fwd_only else args.zero)
+    chain_step = ChainStep(inp, chain, cfg, dev, seed=rank) if chain > 1 else None
 
     def one_step():
-        for _ in range(chain):  # config 3: K chained invocations per training step (runners/ExtraTrainer.py:254-310)
-            step.step()
+        work = None
         if ar_buf is not None and world > 1:
-            dist.all_reduce(ar_buf)
+            # config 5: the parameter-gradient all-reduce DDP issues while the rest of the backward still runs: async on
+            # NCCL's stream, joined at the end of the step
+            work = dist.all_reduce(ar_buf, async_op=True)
+        if chain_step is not None:
+            chain_step.step()  # config 3: a true K-step chain through the autograd op
+        elif fwd_only:
+            step.forward()     # config 1: the forward warp only
+        else:
+            step.step()
+        if work is not None:
+            work.wait()
 
     pix_step = cfg["N"] * cfg["H"] * cfg["W"] * chain
     if sampler:
@@ -395,7 +477,7 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
 
     # ---- --check (default on): the buffers the timed loop just wrote against the stock torch CUDA composition
     pcheck = None
-    if not args.no_check and not args.profile and chain == 1:
+    if not args.no_check and not args.profile and chain == 1 and not fwd_only:
         pcheck = parity_check(step, inp)
     if args.profile:
         if sampler:
@@ -405,7 +487,9 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     # ---- per-kernel durations (same buffers, CUDA events on the launching stream)
     kt = {}
     ksteps = max(10, min(args.steps, 100))
-    if step.fused:  # kernels 2+3 run as one fused launch inside the backward_flow entry point
+    if fwd_only:
+        klist = (("forward", step.forward),)
+    elif step.fused:  # kernels 2+3 run as one fused launch inside the backward_flow entry point
         klist = (("forward", step.forward), ("backward_fused", step.backward_flow))
     else:
         klist = (("forward", step.forward), ("backward_flow", step.backward_flow), ("backward_src", step.backward_src))
@@ -493,6 +577,15 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             regimes[name] = {"ms_per_step": t_r * 1e3, "Gpix_per_s": pixs / t_r / 1e9, "frac_of_hbm_roofline": pixs * BYTES_PER_PIX / t_r / 1e9 / peaks()[0]}
             del st2, alt
 
+    # ---- the headline op through the public autograd API (same tensors, same kernels + the op's host-side cost)
+    via_autograd = None
+    if not fwd_only and chain == 1:
+        ag = AutogradStep(inp)
+        t_ag = sharding.max_over_ranks(timed(ag.step, max(10, min(args.steps, 50)), 3, sync), dev) / max(10, min(args.steps, 50))
+        via_autograd = {"ms_per_step": t_ag * 1e3, "Gpix_per_s": world * cfg["N"] * cfg["H"] * cfg["W"] / t_ag / 1e9,
+                        "api": "deep_video_interpolation_extrapolation_b200.warp_blend + torch.autograd.backward (allocations included)"}
+        del ag
+
     # ---- e2e: public API for HOST buffers (HostWarpBlend: the autograd op per batch chunk, pinned host in -> pinned host
     # out, H2D of every input and D2H of every output / gradient inside the timed region, copies overlapped with compute)
     host_in = [t.cpu().pin_memory() for t in inp["f0"] + inp["f1"] + [inp["ff"], inp["fb"], inp["mf"], inp["mb"]] + inp["gos"]]
@@ -517,28 +610,46 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
         kernels = {k: {"ms": v * 1e3, "bytes_per_pixel": KERNEL_BYTES[k], "GBps": pix_launch * KERNEL_BYTES[k] / v / 1e9,
                        "frac": pix_launch * KERNEL_BYTES[k] / v / 1e9 / peak} for k, v in kt.items()}
         dom = max(kt, key=kt.get)
-        step_gbs = value / world * BYTES_PER_PIX  # per-GPU Gpix/s * B/pix = GB/s
+        # algorithmic bytes per pixel of the timed step: the headline op (808), the forward alone (config 1: 300), or the chain of
+        # config 3 (frames are data: no source gradient at step 0, only the RGB prediction's gradient (12 B) afterwards)
+        C = C_TOTAL
+        if fwd_only:
+            step_bytes = 12 * C + 24
+        elif chain > 1:
+            step_bytes = (12 * C + 24) + (12 * C + 48) + 12.0 * (chain - 1) / chain
+        else:
+            step_bytes = BYTES_PER_PIX
+        step_gbs = value / world * step_bytes  # per-GPU Gpix/s * B/pix = GB/s
+        cfgd = config_dict(cfg, args, world)
+        cfgd.update({"deterministic": bool(args.deterministic), "grad_src_zeroing": step.zero})
+        if chain > 1:
+            cfgd["chain"] = ("true K-step chain through the autograd op: prediction k is a source of step k+1, seg re-one-hotted "
+                             "by argmax, gradient through the RGB prediction, one backward (runners/ExtraTrainer.py:254-310)")
+        if ar_buf is not None:
+            cfgd["allreduce"] = f"{cfg['allreduce']} fp32 parameters, dist.all_reduce(async_op=True) issued before the op, joined after it"
+        launches = (1 if fwd_only else (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]))
+        if chain > 1:  # per chain: step 0 (frames are data) forward + kernel 2; later steps forward (zero-fill) + fused backward
+            launches = 2 * chain
         out = {
             "metric": "warp+blend fwd+bwd Gpix/s", "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
-                       "flow_sigma_px": cfg["sigma"], "chained_steps": chain, "padding_mode": "border", "align_corners": False,
-                       "deterministic": bool(args.deterministic), "grad_src_zeroing": step.zero, "parallelism": f"batch-sharded x{world}, no collective in the op",
-                       "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"},
+            "config": cfgd,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_pixel": KERNEL_BYTES[dom]},
-            "roofline_step": {"bytes_per_pixel": BYTES_PER_PIX, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+            "roofline_step": {"bytes_per_pixel": step_bytes, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
             "kernels": kernels,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "chunk": args.e2e_chunk, "numa_local_cores": numa_cores,
                     "api": "deep_video_interpolation_extrapolation_b200.HostWarpBlend.run (forward + backward C-ABI calls per batch chunk; "
                            "pinned host in/out, H2D | compute | D2H on three streams)"},
-            "gpu_launches": args.steps * chain * (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]),
+            "gpu_launches": args.steps * launches,
             "clocks": clocks,
         }
+        if via_autograd is not None:
+            out["via_autograd"] = via_autograd
         if pcheck is not None:
             out["parity_check"] = pcheck
         if aux:
@@ -553,13 +664,17 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             out["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": cores, "kind": "port",
                                    "sample": f"{reps} reps of {ns} of {cfg['N']} clips, torch {torch.__version__} CPU restatement "
                                              f"of the reference composition (oracle/torch_ref.py), fwd+bwd"}
-        print(json.dumps(out))
+        line = json.dumps(out)
+        print(line)
+        if args.record:  # tracked record of non-default configs (the driver only runs the default one)
+            with open(os.path.join(ROOT, "profiles", "r2_bench_lines.jsonl"), "a") as f:
+                f.write(json.dumps({"label": args.record, **out}) + "\n")
     if world > 1:
         dist.destroy_process_group()
 
 
 # launches of OUR kernels per step (see csrc/flowwarp_b200.cu)
-# fused: fwd_tile_kernel 1 (also zero-fills grad_src) + bwd_tile_kernel 1 (--zero memset: 4 cudaMemsetAsync nodes, not counted);
+# fused: fwd_tex_kernel 1 (also zero-fills grad_src) + bwd_tile_kernel<TEX> 1 (--zero memset: 4 cudaMemsetAsync nodes, not counted);
 # split (deterministic): forward 1 + (table init 1 + emit 1 + kernel 2) + kernel 3 x2
 LAUNCHES_PER_STEP = {"fused": 1 + 1, "split": 1 + 3 + 2}
 
@@ -583,6 +698,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--check", action="store_true", help="(default) compare the timed buffers with the stock torch CUDA composition")
     ap.add_argument("--no-check", action="store_true", help="skip the parity_check of the timed buffers")
+    ap.add_argument("--record", default=None, help="append the JSON line to profiles/r2_bench_lines.jsonl under this label")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu); prints no JSON")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

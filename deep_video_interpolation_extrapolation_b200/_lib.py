@@ -98,6 +98,8 @@ class fwb_label_problem(C.Structure):
 
 LIB_NAME = "libflowwarp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
+if os.environ.get("FWB_LIB"):  # A/B hook: another build of the same library (e.g. different launch bounds)
+    LIB_PATH = os.environ["FWB_LIB"]
 
 # every symbol include/flowwarp_b200.h declares
 SYMBOLS = (

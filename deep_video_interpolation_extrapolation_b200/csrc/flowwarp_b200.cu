@@ -1054,11 +1054,20 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
   int want = 0;
   for (int d = 0; d < p->n_dirs; ++d) want |= (Q.grad_flow[d] || Q.grad_gate[d] || Q.grad_blend[d]);
   if (want) {
-    const dim3 grid = pixel_grid(p), block(NTHREADS);
-    if (p->n_dirs == 2)
-      bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
-    else
-      bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+    TexP X2;
+    if (tex_prepare(p, X2)) {  // kernel 2 on the texture units (dense sources), also in the deterministic split path
+      const dim3 g2((p->W + TXF_TW - 1) / TXF_TW, (p->H + TXF_TH - 1) / TXF_TH, p->N * p->T);
+      if (p->n_dirs == 2)
+        bwd_flow_tex_kernel<2><<<g2, TXF_THREADS, 0, s>>>(P, Q, X2);
+      else
+        bwd_flow_tex_kernel<1><<<g2, TXF_THREADS, 0, s>>>(P, Q, X2);
+    } else {
+      const dim3 grid = pixel_grid(p), block(NTHREADS);
+      if (p->n_dirs == 2)
+        bwd_flow_kernel<2><<<grid, block, 0, s>>>(P, Q);
+      else
+        bwd_flow_kernel<1><<<grid, block, 0, s>>>(P, Q);
+    }
   }
   if ((rc = (int32_t)cudaGetLastError())) return rc;
   if (fused_req) {  // the fused kernel could not take this problem: finish grad_src here, as the flag promises

@@ -55,6 +55,9 @@ __device__ __forceinline__ float* zero_plane(const ZeroP& Z, const Geo& G, int g
 }
 
 constexpr int TXF_THREADS = 256;
+#ifndef TXF_ZERO_FIRST
+#define TXF_ZERO_FIRST 1  // zero-fill side job before (1) or after (0) the channel loop
+#endif
 constexpr int TXF_CB = 4;  // channels per batch of texture fetches
 constexpr int TXF_TW = 32, TXF_TH = 8;  // CTA tile: 4 x 2 warp patches of 8 x 4 pixels
 
@@ -78,6 +81,20 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
     t = blockIdx.z - n * G.T;
   }
   const bool in = j < G.W && i < G.H;
+#if TXF_ZERO_FIRST
+  if (Z.on) {  // 64 float4 per plane and tile: a quarter of the CTA per plane, planes round robin
+    const int f4 = threadIdx.x & 63, zi = blockIdx.y * TXF_TH + (f4 >> 3), zj = blockIdx.x * TXF_TW + (f4 & 7) * 4;
+    if (zi < G.H && zj < G.W) {
+      for (int pl = threadIdx.x >> 6; pl < Ctot * NDIRS; pl += TXF_THREADS / 64) {
+        const int cf = pl / NDIRS, d = pl - cf * NDIRS;
+        int g, c;
+        chan_lookup(P, cf, g, c);
+        float* zp = zero_plane(Z, G, g, d, n, t, c);
+        if (zp) *reinterpret_cast<float4*>(zp + (long long)zi * Z.sh[d] + zj) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+#endif
   float w[NDIRS][4], bl[NDIRS], fx1[NDIRS], fy1[NDIRS];
   unsigned v[NDIRS];
   bool has_bl[NDIRS];
@@ -137,6 +154,7 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
       }
     }
   }
+#if !TXF_ZERO_FIRST
   if (Z.on) {  // 64 float4 per plane and tile: a quarter of the CTA per plane, planes round robin
     const int f4 = threadIdx.x & 63, zi = blockIdx.y * TXF_TH + (f4 >> 3), zj = blockIdx.x * TXF_TW + (f4 & 7) * 4;
     if (zi < G.H && zj < G.W) {
@@ -149,6 +167,7 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
       }
     }
   }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

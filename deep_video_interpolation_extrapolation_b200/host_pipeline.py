@@ -25,6 +25,31 @@ from .sharding import chunk_slices
 Tensor = torch.Tensor
 
 
+def _numel(shape) -> int:
+    n = 1
+    for x in shape:
+        n *= int(x)
+    return n
+
+
+def chunk_layout(n: int, Cs: Sequence[int], H: int, W: int):
+    """Shapes, in arena order, of the inputs and of the results of one chunk of n clips:
+    inputs  frames0[g].., frames1[g].., for_flow, back_flow, for_mask, back_mask, grad_outs[g]..
+    results outs[g].., grad_frames0[g].., grad_frames1[g].., grad_for_flow, grad_back_flow, grad_for_mask, grad_back_mask"""
+    fr = [(n, c, H, W) for c in Cs]
+    fl, mk = [(n, 2, H, W)] * 2, [(n, 1, H, W)] * 2
+    return [*fr, *fr, *fl, *mk, *fr], [*fr, *fr, *fr, *fl, *mk]
+
+
+def _carve(buf: Tensor, shapes) -> List[Tensor]:
+    out, off = [], 0
+    for sh in shapes:
+        k = _numel(sh)
+        out.append(buf[off:off + k].view(*sh))
+        off += k
+    return out
+
+
 class _Slot:
     """Device buffers of one in-flight chunk (inputs, outputs, gradients, workspace) and its C-ABI structs.  Preallocated
     once: the timed path neither allocates nor frees (no caching-allocator traffic between the three streams)."""
@@ -32,16 +57,22 @@ class _Slot:
     def __init__(self, dev, n, Cs, H, W, kw):
         f32 = dict(dtype=torch.float32, device=dev)
         self.n = n
-        self.f0 = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.f1 = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.flows = [torch.empty(n, 2, 1, H, W, **f32) for _ in range(2)]
-        self.masks = [torch.empty(n, 1, H, W, **f32) for _ in range(2)]
-        self.gos = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.outs = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.g_f0 = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.g_f1 = [torch.empty(n, 1, c, H, W, **f32) for c in Cs]
-        self.g_flows = [torch.empty(n, 2, 1, H, W, **f32) for _ in range(2)]
-        self.g_masks = [torch.empty(n, 1, H, W, **f32) for _ in range(2)]
+        # every input of a chunk lives in ONE device buffer and every result in another, in the order and at the offsets of
+        # the host arenas (chunk_layout): a chunk moves with one cudaMemcpyAsync each way
+        in_shapes, out_shapes = chunk_layout(n, Cs, H, W)
+        self.in_buf = torch.empty(sum(_numel(sh) for sh in in_shapes), **f32)
+        self.out_buf = torch.empty(sum(_numel(sh) for sh in out_shapes), **f32)
+        iv, ov = _carve(self.in_buf, in_shapes), _carve(self.out_buf, out_shapes)
+        G = len(Cs)
+        u5 = lambda t: t.unsqueeze(1)  # noqa: E731  [n,C,H,W] -> [n,1,C,H,W]
+        self.f0, self.f1 = [u5(t) for t in iv[:G]], [u5(t) for t in iv[G:2 * G]]
+        self.flows = [t.unsqueeze(2) for t in iv[2 * G:2 * G + 2]]
+        self.masks = list(iv[2 * G + 2:2 * G + 4])
+        self.gos = [u5(t) for t in iv[2 * G + 4:]]
+        self.outs = [u5(t) for t in ov[:G]]
+        self.g_f0, self.g_f1 = [u5(t) for t in ov[G:2 * G]], [u5(t) for t in ov[2 * G:3 * G]]
+        self.g_flows = [t.unsqueeze(2) for t in ov[3 * G:3 * G + 2]]
+        self.g_masks = list(ov[3 * G + 2:3 * G + 4])
         self.ev_cmp = torch.cuda.Event()  # compute of the chunk that last used this slot is done (inputs free)
         self.ev_out = torch.cuda.Event()  # its results have left the device (outputs / gradients free)
         self.used = False
@@ -117,6 +148,9 @@ class HostWarpBlend:
         self._key = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._arena_in: Optional[Tensor] = None   # [chunks, floats per chunk] pinned: all inputs of a chunk back to back
+        self._arena_out: Optional[Tensor] = None  # [chunks, floats per chunk] pinned: all results of a chunk back to back
+        self._arena_key = None
 
     def _setup(self, key, N, Cs, H, W):
         if self._key == key:
@@ -198,6 +232,87 @@ class HostWarpBlend:
         if synchronize:
             self.done.synchronize()
         return res
+
+    # ------------------------------------------------------------------ arena mode: one copy per chunk and direction
+    def arena(self, N: int, Cs: Sequence[int], H: int, W: int) -> Dict[str, object]:
+        """Pinned host ARENAS for a batch of N clips: the producer (data loader / previous stage) writes its tensors straight
+        into the returned per-chunk views and reads the results from them, so that `run_arena()` moves every chunk with ONE
+        cudaMemcpyAsync host->device and ONE device->host instead of 13 + 11 (the per-tensor path of `run`).
+
+        Returns {"inputs": [per chunk: list of views in chunk_layout order], "results": [per chunk: list of views],
+                 "chunks": [slice of the batch each chunk covers]}.  The last chunk may be ragged: its views hold m < chunk clips
+        (the arena row is still laid out for a full chunk)."""
+        Cs = tuple(int(c) for c in Cs)
+        key = (N, Cs, H, W)
+        n = min(self.chunk, max(N, 1))
+        sls = chunk_slices(N, n)
+        if self._arena_key != key:
+            self._setup(key, N, Cs, H, W)
+            in_shapes, out_shapes = chunk_layout(n, Cs, H, W)
+            fi, fo = sum(_numel(s) for s in in_shapes), sum(_numel(s) for s in out_shapes)
+            self._arena_in = torch.empty((max(len(sls), 1), fi), dtype=torch.float32).pin_memory()
+            self._arena_out = torch.empty((max(len(sls), 1), fo), dtype=torch.float32).pin_memory()
+            self._arena_key = key
+        in_shapes, out_shapes = chunk_layout(n, Cs, H, W)
+        ins, outs = [], []
+        for k, sl in enumerate(sls):
+            m = sl.stop - sl.start
+            ins.append([v[:m] for v in _carve(self._arena_in[k], in_shapes)])
+            outs.append([v[:m] for v in _carve(self._arena_out[k], out_shapes)])
+        return {"inputs": ins, "results": outs, "chunks": sls}
+
+    def fill_arena(self, frames0, frames1, for_flow, back_flow, for_mask, back_mask, grad_outs) -> Dict[str, object]:
+        """Convenience (CPU copies): place ordinary host tensors ([N,...]) into the arena.  A real producer writes the views."""
+        N, _, H, W = for_flow.shape
+        a = self.arena(N, [int(t.shape[1]) for t in frames0], H, W)
+        host = [*frames0, *frames1, for_flow, back_flow, for_mask, back_mask, *grad_outs]
+        for views, sl in zip(a["inputs"], a["chunks"]):
+            for v, t in zip(views, host):
+                v.copy_(t[sl])
+        return a
+
+    def run_arena(self, synchronize: bool = True):
+        """forward + backward of the batch that sits in the arena (see `arena`): per chunk ONE H2D copy of its inputs, the
+        three C-ABI calls, ONE D2H copy of its results; H2D | compute | D2H of consecutive chunks overlap on three streams."""
+        if self._arena_key is None:
+            raise RuntimeError("HostWarpBlend.run_arena: call arena(...) / fill_arena(...) first")
+        N = self._arena_key[0]
+        sls = chunk_slices(N, min(self.chunk, max(N, 1)))
+        self.h2d_bytes = len(sls) * self._arena_in.shape[1] * 4
+        self.d2h_bytes = len(sls) * self._arena_out.shape[1] * 4
+        if N == 0:
+            return
+        dev = self.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            for s in (self.s_in, self.s_cmp, self.s_out):
+                s.wait_stream(cur)
+            for k, sl in enumerate(sls):
+                slot = self._slots[k % len(self._slots)]
+                m = sl.stop - sl.start
+                with torch.cuda.stream(self.s_in):
+                    if slot.used:
+                        self.s_in.wait_event(slot.ev_cmp)
+                    slot.in_buf.copy_(self._arena_in[k], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(self.s_in)
+                with torch.cuda.stream(self.s_cmp):
+                    self.s_cmp.wait_event(ev_in)
+                    if slot.used:
+                        self.s_cmp.wait_event(slot.ev_out)
+                    slot.launch(m, self.s_cmp.cuda_stream)
+                    slot.ev_cmp.record(self.s_cmp)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(slot.ev_cmp)
+                    self._arena_out[k].copy_(slot.out_buf, non_blocking=True)
+                    slot.ev_out.record(self.s_out)
+                slot.used = True
+            self.done.record(self.s_out)
+            cur.wait_stream(self.s_out)
+            cur.wait_stream(self.s_cmp)
+            cur.wait_stream(self.s_in)
+        if synchronize:
+            self.done.synchronize()
 
     @staticmethod
     def _flat(res) -> List[Tensor]:

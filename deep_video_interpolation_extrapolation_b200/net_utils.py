@@ -7,7 +7,9 @@ in place of the originals:
     FlowWrapper            utils/net_utils.py:89-114   parameter-free nn.Module, forward(x, flow)
     warp                   utils/net_utils.py:116-121  -> [N,T,C,H,W], flow gated by mask
     warp_back              utils/net_utils.py:124-129  per-frame source, flow sign flipped
+    refine                 utils/net_utils.py:131-147  same signature; the per-frame blend is one streaming kernel
     blend_with_noise       utils/net_utils.py:141-143  input*mask + noise*(1-mask)  (the `refine` pre-blend)
+    warp_cat               nets/VAE_S.py:134-135,141   warp of several channel groups into ONE concatenated tensor
     bidirectional_warp     nets/OpticalUnet.py:123-146 forward/backward warps, border padding, mask weighting
     warp_blend             the same two warps fused with their mask-weighted sum (the synthesized frame)
 
@@ -85,6 +87,26 @@ def warp_multi(frames: Sequence[Tensor], flow: Tensor, opt, flowwarpper, mask: T
     the 20-channel seg map with identical flow/mask in two calls): coordinates are computed once."""
     T = _check_T(opt, flow)
     return flow_warp_blend(list(frames), [flow[:, :, :T]], gates=[mask[:, :T]], signs=-1.0, **_opts(flowwarpper))
+
+
+def warp_cat(frames: Sequence[Tensor], flow: Tensor, opt, flowwarpper, mask: Tensor) -> Tensor:
+    """`torch.cat([warp(f, flow, opt, floww, mask) for f in frames], dim=2)` (nets/VAE_S.py:134-135,141: the RGB and seg warps
+    concatenated for the refine net) as ONE launch writing one [N,T,sum(C),H,W] tensor: no per-group outputs, no cat copy."""
+    T = _check_T(opt, flow)
+    return flow_warp_blend(list(frames), [flow[:, :, :T]], gates=[mask[:, :T]], signs=-1.0, concat=True, **_opts(flowwarpper))[0]
+
+
+def refine(input: Tensor, flow: Tensor, mask: Tensor, refine_net, opt, noise_bg: Tensor) -> Tensor:
+    """Drop-in for utils/net_utils.py:131-147 (same signature, same result).
+
+    The reference blends every frame with four pointwise kernels inside a Python loop (`input[:, i] * mask[:, i:i+1] +
+    noise * (1 - mask[:, i:i+1])`, after `cat([noise_bg, zeros(bs, 20, h, w)])` when opt.seg); here all T frames are blended
+    by one streaming kernel (channels beyond noise_bg's blend against zero: bit-identical to the cat with zeros), then
+    `refine_net` runs per frame exactly as in the reference (:141-144) and the results are concatenated (:146)."""
+    T = int(opt.vid_length)
+    blended = mask_blend(input[:, :T], mask[:, :T], noise_bg)
+    out = [torch.unsqueeze(refine_net(blended[:, i], flow[:, :, i, :, :]), 1) for i in range(T)]
+    return torch.cat(out, 1)
 
 
 def blend_with_noise(input: Tensor, mask: Tensor, noise: Tensor) -> Tensor:

@@ -51,6 +51,7 @@ class _Cfg:
     T: int
     H: int
     W: int
+    concat: bool = False  # one [N,T,sum(C),H,W] output, the groups' channels back to back (nets/VAE_S.py:141's torch.cat)
 
 
 def _ptr(x: Tensor) -> int:
@@ -80,9 +81,10 @@ def _stream_ptr(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def _alloc_grad_src(s: Tensor, cfg) -> Tensor:
-    """grad buffer of source `s` ([N,T,C,H,W]; T-stride 0 = one frame shared by all T -> one summed plane set)."""
-    shared = s.stride(1) == 0 and cfg.T > 1
+def _alloc_grad_src(s: Tensor, cfg, shared: bool) -> Tensor:
+    """grad buffer of source `s` ([N,T,C,H,W]).  shared: the op itself broadcast a single frame [N,1,C,H,W] over the T flows
+    (utils/net_utils.py:118) -> one plane set the kernels sum into (T-stride 0).  A source the CALLER expanded to [N,T,...]
+    keeps a per-frame gradient: autograd's own expand backward sums it."""
     buf = torch.empty((cfg.N, 1 if shared else cfg.T, s.shape[2], cfg.H, cfg.W), dtype=torch.float32, device=s.device)
     return buf.expand(cfg.N, cfg.T, s.shape[2], cfg.H, cfg.W) if shared else buf
 
@@ -95,10 +97,17 @@ class _WarpBlendFn(torch.autograd.Function):
         D, G = cfg.n_dirs, cfg.n_groups
         tensors = tuple(_wcontig(t) for t in tensors)
         flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        shared = [[s.shape[1] == 1 and cfg.T > 1 for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
         srcs = [[_expand_t(s, cfg.T) for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
         dev = flows[0].device
-        outs = [torch.empty((cfg.N, cfg.T, srcs[g][0].shape[2], cfg.H, cfg.W), dtype=torch.float32, device=dev)
-                for g in range(G)]
+        if cfg.concat:  # the kernels take per-group strides: every group writes its channel slice of ONE buffer
+            Cs = [srcs[g][0].shape[2] for g in range(G)]
+            big = torch.empty((cfg.N, cfg.T, sum(Cs), cfg.H, cfg.W), dtype=torch.float32, device=dev)
+            offs = [sum(Cs[:g]) for g in range(G)]
+            outs = [big[:, :, offs[g]:offs[g] + Cs[g]] for g in range(G)]
+        else:
+            outs = [torch.empty((cfg.N, cfg.T, srcs[g][0].shape[2], cfg.H, cfg.W), dtype=torch.float32, device=dev)
+                    for g in range(G)]
         lib = L.load()
         with torch.cuda.device(dev):
             p = fill_problem(N=cfg.N, T=cfg.T, H=cfg.H, W=cfg.W, flows=flows, gates=gates, blends=blends,
@@ -109,7 +118,7 @@ class _WarpBlendFn(torch.autograd.Function):
             need_src = ctx.needs_input_grad[1 + 3 * D:]
             pre = None
             if PREZERO_GRAD_SRC and _flags(cfg) == L.FWB_FLAG_FUSED_BWD and any(need_src):
-                pre = [[_alloc_grad_src(srcs[g][d], cfg) if need_src[g * D + d] else None for d in range(D)]
+                pre = [[_alloc_grad_src(srcs[g][d], cfg, shared[g][d]) if need_src[g * D + d] else None for d in range(D)]
                        for g in range(G)]
                 q = fill_grads(p, grad_outs=[None] * G, grad_srcs=pre, grad_flows=[None] * D, grad_gates=[None] * D,
                                grad_blends=[None] * D, ptr=_ptr, strides=_strides)
@@ -121,7 +130,7 @@ class _WarpBlendFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.save_for_backward(*[t for t in tensors if t is not None])
         ctx.present = [t is not None for t in tensors]
-        return tuple(outs)
+        return (big,) if cfg.concat else tuple(outs)
 
     @staticmethod
     @once_differentiable  # the gradients are computed by CUDA kernels autograd cannot see through: no silent double backward
@@ -131,11 +140,18 @@ class _WarpBlendFn(torch.autograd.Function):
         it = iter(ctx.saved_tensors)
         tensors = [next(it) if pr else None for pr in ctx.present]
         flows, gates, blends = tensors[:D], tensors[D:2 * D], tensors[2 * D:3 * D]
+        shared = [[s.shape[1] == 1 and cfg.T > 1 for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
         srcs = [[_expand_t(s, cfg.T) for s in tensors[3 * D + g * D: 3 * D + (g + 1) * D]] for g in range(G)]
         need = ctx.needs_input_grad[1:]
         dev = flows[0].device
         N, T, H, W = cfg.N, cfg.T, cfg.H, cfg.W
 
+        if cfg.concat:  # one upstream gradient for the concatenated output: channel-slice views, no copy
+            if grad_outs[0] is None:
+                return (None,) + (None,) * len(tensors)
+            gcat = _wcontig(grad_outs[0])
+            Cs = [srcs[g][0].shape[2] for g in range(G)]
+            grad_outs = tuple(gcat[:, :, sum(Cs[:g]):sum(Cs[:g + 1])] for g in range(G))
         gos = [None if g is None else _wcontig(g) for g in grad_outs]
         if all(g is None for g in gos):
             return (None,) + (None,) * len(tensors)
@@ -151,7 +167,7 @@ class _WarpBlendFn(torch.autograd.Function):
             row = []
             for d in range(D):
                 if need[3 * D + g * D + d] and gos[g] is not None:
-                    row.append(pre[g][d] if pre is not None else _alloc_grad_src(srcs[g][d], cfg))
+                    row.append(pre[g][d] if pre is not None else _alloc_grad_src(srcs[g][d], cfg, shared[g][d]))
                 else:
                     row.append(None)
             g_srcs.append(row)
@@ -182,7 +198,7 @@ class _WarpBlendFn(torch.autograd.Function):
         for g in range(G):
             for d in range(D):
                 x = g_srcs[g][d]
-                if x is not None and x.stride(1) == 0 and T > 1:
+                if x is not None and shared[g][d]:
                     x = x[:, :1]  # the kernel already summed over the T frames that share this source
                 flat_src.append(x)
         return (None, *g_flows, *g_gates, *g_blends, *flat_src)
@@ -224,6 +240,7 @@ def flow_warp_blend(
     padding_mode: str = "zeros",
     align_corners: bool = False,
     deterministic: bool = False,
+    concat: bool = False,
 ) -> List[Tensor]:
     """out[g] = sum_d blend_d * grid_sample(srcs[g][d], base + sign_d * flow_d * gate_d).
 
@@ -233,6 +250,8 @@ def flow_warp_blend(
     gates   per direction or None; flow-gating mask (utils/net_utils.py:118)
     blends  per direction or None; blend weight of that direction's warp (nets/OpticalUnet.py:141-146)
     signs   per direction, -1 (`base - flow`, default) or +1 (`base + flow`)
+    concat  write all groups into ONE tensor, channels back to back (the `torch.cat([output, output_seg], dim=2)` of
+            nets/VAE_S.py:141 without the copy); the returned list then has that single tensor
     Returns one [N,C,H,W] (all inputs 4-D) or [N,T,C,H,W] tensor per group.
     """
     if isinstance(flows, Tensor):
@@ -310,9 +329,11 @@ def flow_warp_blend(
 
     if N == 0:  # nothing to launch (empty tensors have no storage to point the C-ABI at)
         outs = [s.new_empty((0, T, s.shape[2], H, W)) for s in (row[0] for row in csrcs)]
+        if concat:
+            outs = [torch.cat(outs, 2)]
         return outs if five_d else [o.squeeze(1) for o in outs]
     cfg = _Cfg(D, G, signs, L.FWB_PAD_BORDER if padding_mode == "border" else L.FWB_PAD_ZEROS,
-               bool(align_corners), bool(deterministic), N, T, H, W)
+               bool(align_corners), bool(deterministic), N, T, H, W, bool(concat))
     flat = [*cflows, *cgates, *cblends, *[s for row in csrcs for s in row]]
     outs = list(_WarpBlendFn.apply(cfg, *flat))
     if not five_d:

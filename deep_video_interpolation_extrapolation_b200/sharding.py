@@ -79,3 +79,38 @@ def bind_to_gpu_numa(device_index: int) -> int:
         return len(cpus)
     except Exception:  # noqa: BLE001 - best effort: the binding is an optimisation, never a requirement
         return 0
+
+
+def sync(loss_dict, mean: bool = True, world: int | None = None):
+    """Drop-in for the trainers' `sync(loss_dict, mean)` (runners/InterTrainer.py:859-864, ExtraTrainer.py:760-765): every
+    tensor of `loss_dict` is all-reduced in place and, with `mean`, divided by the number of ranks.
+
+    The reference issues ONE `dist.all_reduce` (+ one `div_`) per scalar loss — ~40 latency-bound NCCL launches per step
+    (SURVEY 8f row 4).  Here all values are flattened into one buffer per (device, dtype), reduced with ONE collective and
+    scattered back, so the cost is one launch latency regardless of how many losses the dictionary holds.  Results are
+    identical to the per-tensor loop (the same sum per element; the division is the same elementwise op).  `world`
+    defaults to the process group's size (the reference divides by `args.gpus`)."""
+    import torch
+    import torch.distributed as dist
+    tensors = [t for t in loss_dict.values() if isinstance(t, torch.Tensor)]
+    if not tensors:
+        return loss_dict
+    on = dist.is_available() and dist.is_initialized()
+    if world is None:
+        world = dist.get_world_size() if on else 1
+    groups = {}
+    for t in tensors:
+        groups.setdefault((t.device, t.dtype), []).append(t)
+    for (_, _), ts in groups.items():
+        flat = torch.cat([t.detach().reshape(-1) for t in ts])
+        if on and dist.get_world_size() > 1:
+            dist.all_reduce(flat)
+        if mean:
+            flat.div_(world)
+        off = 0
+        with torch.no_grad():
+            for t in ts:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))
+                off += n
+    return loss_dict

@@ -641,6 +641,53 @@ def test_mask_blend_vs_reference_refine_golden(pkg, golden_dir, name):
     assert relerr(tn.grad, z["grad_noise"]) <= BWD_TOL
 
 
+@pytest.mark.parametrize("name", ["refine_0.npz", "refine_1.npz"])
+def test_refine_drop_in_signature_vs_reference_golden(pkg, golden_dir, name):
+    """refine(input, flow, mask, refine_net, opt, noise_bg) — the reference's own signature (utils/net_utils.py:131-147) with
+    an identity refine_net, against the committed outputs of the unmodified reference: bit-exact forward."""
+    z = np.load(os.path.join(golden_dir, name))
+    N, T, C, H, W = z["shape"]
+    s = z["seeds"]
+    ti = cu(synth.grad(s[0], (N, T, C, H, W)), True)
+    tm = cu(synth.mask(s[1], N, H, W, T=T), True)
+    tn = cu(synth.rgb(s[2], N, H, W, 3), True)
+    opt = types.SimpleNamespace(vid_length=int(T), seg=bool(C > 3))
+    seen = []
+
+    def refine_net(x, flow):  # identity, as in tests/golden/make_golden_refine.py; records the per-frame calls
+        seen.append((tuple(x.shape), tuple(flow.shape)))
+        return x
+
+    out = pkg.refine(ti, torch.zeros(N, 2, T, H, W, device="cuda"), tm, refine_net, opt, tn)
+    assert seen == [((N, C, H, W), (N, 2, H, W))] * T
+    assert np.array_equal(out.detach().cpu().numpy(), z["out"])
+    out.backward(cu(synth.grad(s[3], (N, T, C, H, W))))
+    assert relerr(ti.grad, z["grad_input"]) <= BWD_TOL and relerr(tm.grad, z["grad_mask"]) <= BWD_TOL
+    assert relerr(tn.grad, z["grad_noise"]) <= BWD_TOL
+
+
+@pytest.mark.parametrize("det", [False, True])
+def test_warp_cat_equals_cat_of_warps(pkg, det):
+    """warp_cat (one launch into one [N,T,3+20,H,W] buffer) == torch.cat([warp(rgb), warp(seg)], dim=2) (nets/VAE_S.py:134-141),
+    forward bit for bit, gradients within the bar."""
+    N, T, H, W = 2, 3, 40, 64
+    rgb, seg = synth.rgb(0, N, H, W, 3), synth.seg(1, N, H, W, 20)
+    fl, m = synth.flow(2, N, H, W, 5.0, T=T), synth.mask(3, N, H, W, T=T)
+    go = synth.grad(4, (N, T, 23, H, W))
+    opt = types.SimpleNamespace(vid_length=T)
+    fw = pkg.FlowWrapper(deterministic=det)
+    a = [cu(rgb, True), cu(seg, True), cu(fl, True), cu(m, True)]
+    ref = torch.cat([pkg.warp(a[0], a[2], opt, fw, a[3]), pkg.warp(a[1], a[2], opt, fw, a[3])], dim=2)
+    ref.backward(cu(go))
+    b = [cu(rgb, True), cu(seg, True), cu(fl, True), cu(m, True)]
+    out = pkg.warp_cat([b[0], b[1]], b[2], opt, fw, b[3])
+    assert out.shape == (N, T, 23, H, W) and out.is_contiguous()
+    assert torch.equal(out, ref)
+    out.backward(cu(go))
+    for x, y in zip(a, b):
+        assert relerr(y.grad, x.grad) <= BWD_TOL
+
+
 # ---------------------------------------------------------------- compact segmentation format: uint8 labels
 def _labels(seed, N, H, W, K=20, T=None):
     rng = np.random.default_rng(seed)
@@ -818,3 +865,19 @@ def test_c_abi_calls_are_cuda_graph_capturable(pkg, det):
     torch.cuda.synchronize()
     for a, b in zip(eager, slot.results()):
         assert torch.equal(a, b) if det else relerr(b, a) <= BWD_TOL
+
+
+def test_caller_expanded_source_keeps_per_frame_gradient(pkg, oracle):
+    """A source the CALLER expanded over T ([N,1,C,H,W].expand(-1,T,...), T-stride 0) is an [N,T,...] autograd input: the op
+    returns a per-frame gradient and autograd's expand backward sums it (the op used to return [N,1,...])."""
+    N, T, H, W = 2, 3, 40, 64
+    x = synth.seg(1, N, H, W, 4)
+    fl, m = synth.flow(2, N, H, W, 5.0, T=T), synth.mask(3, N, H, W, T=T)
+    go = synth.grad(4, (N, T, 4, H, W))
+    for det in (False, True):
+        xt = cu(x, True)
+        xe = xt.unsqueeze(1).expand(-1, T, -1, -1, -1)
+        out = pkg.flow_warp_blend([xe], [cu(fl)], gates=[cu(m)], deterministic=det)[0]
+        out.backward(cu(go))
+        rg = oracle.backward([x], [fl], [go], gates=[m])
+        assert relerr(xt.grad, rg["grad_srcs"][0][0].sum(axis=1)) <= BWD_TOL

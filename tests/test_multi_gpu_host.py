@@ -109,3 +109,48 @@ def test_numa_binding_is_best_effort_without_a_gpu():
     if n == 0:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    names = [f"step_{i}_loss" for i in range(12)]
+    mine = {k: torch.randn((), generator=g) if i % 3 else torch.randn(3, generator=g) for i, k in enumerate(names)}
+    mine["count"] = torch.tensor(float(rank + 1), dtype=torch.float64)  # a second dtype: its own flat buffer
+    ref = {k: v.clone() for k, v in mine.items()}
+    for t in ref.values():  # the reference's loop: one all_reduce (+ div_) per tensor (runners/InterTrainer.py:859-864)
+        dist.all_reduce(t)
+        t.div_(world)
+    out = sharding.sync(mine, mean=True)
+    assert out is mine
+    same = all(torch.equal(mine[k], ref[k]) for k in mine)
+    summed = sharding.sync({"x": torch.tensor([1.0, 2.0]) * (rank + 1)}, mean=False)["x"]
+    ok_sum = torch.equal(summed, torch.tensor([1.0, 2.0]) * sum(range(1, world + 1)))
+    if rank == 0:
+        q.put((same, ok_sum))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_coalesced_sync_equals_per_tensor_all_reduce():
+    """sharding.sync (one flat all-reduce per dtype) == the reference's per-scalar loop, world_size 2 on gloo."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same, ok_sum = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    assert same and ok_sum
+
+
+def test_sync_without_process_group_is_identity_mean():
+    d = {"a": torch.tensor(3.0), "b": torch.tensor([1.0, 2.0])}
+    sharding.sync(d, mean=True)
+    assert float(d["a"]) == 3.0 and d["b"].tolist() == [1.0, 2.0]
