@@ -20,6 +20,7 @@
 #include "fwb_generic.cuh"
 #include "fwb_owner.cuh"
 #include "fwb_tile.cuh"
+#include "fwb_cl.cuh"
 #include "fwb_bwdx.cuh"
 #include "fwb_blend.cuh"
 #include "fwb_label.cuh"
@@ -297,10 +298,10 @@ static dim3 pixel_grid(const fwb_problem* p) {
 //   backward, determ.  generic kernel 2 + owner-gather kernel 3
 // FWB_KERNELS=<comma separated words> and the FWB_TILE_* sizes switch variants for A/B measurements and for the tests that
 // keep every variant parity-checked.  The environment is read ONCE per process (thread-safe); fwb_reload_env() re-reads it.
-enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u, KN_NOTEX = 256u, KN_SORTED = 512u };
+enum : unsigned { KN_NOFUSE = 8u, KN_GENERIC = 16u, KN_NOTILE = 32u, KN_NOZFUSE = 128u, KN_NOTEX = 256u, KN_SORTED = 512u, KN_NOCL = 1024u };
 struct EnvCfg {
   unsigned knobs;
-  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwdx_kb, tile_bwd_ppt, bwdx_ppt;
+  int tile_fwd_kb, tile_bwd_kb, tile_bwdf_kb, tile_bwdx_kb, tile_bwd_ppt, bwdx_ppt, cl_kb, cl_minc;
 };
 static EnvCfg g_env;
 static std::atomic<int> g_env_ready{0};
@@ -320,6 +321,7 @@ static void env_load_locked() {
     if (strstr(v, "nozfuse")) e.knobs |= KN_NOZFUSE;
     if (strstr(v, "notex")) e.knobs |= KN_NOTEX;
     if (strstr(v, "sorted")) e.knobs |= KN_SORTED;
+    if (strstr(v, "nocl")) e.knobs |= KN_NOCL;
   }
   e.tile_bwd_ppt = env_int("FWB_TILE_BWD_PPT", 2);
   e.tile_fwd_kb = env_int("FWB_TILE_FWD_KB", 52);
@@ -327,6 +329,8 @@ static void env_load_locked() {
   e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
   e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 46);
   e.bwdx_ppt = env_int("FWB_BWDX_PPT", 2);
+  e.cl_kb = env_int("FWB_CL_KB", 94);
+  e.cl_minc = env_int("FWB_CL_MINC", 12);
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
 }
@@ -1000,6 +1004,40 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
 #undef FWB_LAUNCH_SRT
           }
           return (int32_t)cudaGetLastError();
+        }
+        int Cgo = 0;
+        for (int gi = 0; gi < p->n_groups; ++gi)
+          if (Q.grad_out[gi]) Cgo += p->grp[gi].C;
+        if (tex && any_src && !(knobs() & KN_NOCL) && Cgo >= env().cl_minc && Cgo <= CL_MAXC) {
+          // channel-per-lane scatter + kernel 2 on the texture units, warp-specialised (fwb_cl.cuh): the default for wide
+          // channel sets (lanes = channels: a narrow set leaves most lanes idle, the pixel-per-lane kernel below serves it)
+          const int gos_b = 4 * ((Cgo * CL_GS + 3) & ~3);
+          const int dyn = env().cl_kb * 1024;
+          const int acc_words = (dyn - gos_b - 16 - 4 * CL_SLOTS * (CL_NPIX / 2)) / 4;  // slack after the last plane
+          bool cl_fits = acc_words >= (Cgo + 1) * (CL_ZPAD + 64);
+          for (int gi = 0; gi < p->n_groups; ++gi)
+            if (Q.grad_out[gi] && (long long)Q.go_sc[gi] * p->grp[gi].C >= 2147483647LL) cl_fits = false;
+          if (cl_fits) {
+            const dim3 gc((p->W + CL_TW - 1) / CL_TW, (p->H + CL_TH - 1) / CL_TH, p->N * p->T);
+#define FWB_LAUNCH_CL(D, A, B)                                                \
+  do {                                                                        \
+    if ((rc = set_smem(bwd_cl_kernel<D, A, B>, dyn))) return rc;              \
+    bwd_cl_kernel<D, A, B><<<gc, CL_THREADS, dyn, s>>>(P, Q, X, acc_words);   \
+  } while (0)
+            const int keyc = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
+            switch (keyc) {
+              case 0: FWB_LAUNCH_CL(1, false, false); break;
+              case 1: FWB_LAUNCH_CL(1, false, true); break;
+              case 2: FWB_LAUNCH_CL(1, true, false); break;
+              case 3: FWB_LAUNCH_CL(1, true, true); break;
+              case 4: FWB_LAUNCH_CL(2, false, false); break;
+              case 5: FWB_LAUNCH_CL(2, false, true); break;
+              case 6: FWB_LAUNCH_CL(2, true, false); break;
+              default: FWB_LAUNCH_CL(2, true, true); break;
+            }
+#undef FWB_LAUNCH_CL
+            return (int32_t)cudaGetLastError();
+          }
         }
         const int sb = env().tile_bwd_kb * 1024;
         const dim3 grid((p->W + TL_TW - 1) / TL_TW, (p->H + 8 * ppt - 1) / (8 * ppt), p->N * p->T);

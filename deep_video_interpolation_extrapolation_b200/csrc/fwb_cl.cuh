@@ -1,0 +1,616 @@
+// fwb_cl.cuh — fused backward (kernels 2+3) with a CHANNEL-PER-LANE scatter.
+//
+// The scatter of grad_out * weight into grad_src (ATen grid_sampler_2d_backward's atomicAdd, reached from
+// utils/net_utils.py:113) was bound by same-bank serialisation when a warp instruction carried 32 PIXELS of one channel:
+// neighbouring pixels hit the same / neighbouring source cells (3.8 wavefronts per ATOMS).  Here a
+// warp instruction carries the <= 32 CHANNELS of ONE (pixel, direction): lane c adds into plane c of a shared-memory copy of
+// the tile's source footprint, the planes are an odd number of words apart, so the 23 lanes of the headline op always hit
+// 23 different banks: one wavefront per ATOMS, and one descriptor (4 weights + 2 offsets, broadcast loads) serves all
+// channels of the item.  The coordinate gradient (kernel 2) needs the opposite mapping (a thread sums over the channels of
+// its pixel) and runs on the TEXTURE units (fwb_tex.cuh), so the CTA is warp-specialised:
+//
+//     warps 0-7   (thread = pixel)     taps, footprint tables, item descriptors | kernel 2: TLD4 quads x grad_out -> grad_flow ...
+//     warps 8-15  (lane = channel)     grad_out tile -> shared memory, scale vote | scatter (ATOMS.ADD.S32) | flush (RED.F32)
+//
+// and the texture pipe and the shared-memory pipe of an SM are busy at the same time.  A CTA owns a 32x8 tile of output pixels
+// of one (n, t); 2 CTAs per SM.  The two directions are scattered one after the other into the same accumulator planes.
+// Fixed point as in fwb_tile.cuh: scale per channel and tile 2^(20 - exponent(max|grad_out| * max|blend|)),
+// float -> int by fma(x, y, 1.5 * 2^23); non-finite grad_out channels and items whose taps are far from the rest of the tile
+// (border-clamped outliers, or a direction whose footprint does not fit) go to global memory with float atomics.
+#pragma once
+#include "fwb_coords.cuh"
+#include "fwb_generic.cuh"
+#include "fwb_tex.cuh"
+#include "fwb_util.cuh"
+
+namespace fwb {
+
+constexpr int CL_TW = 32, CL_TH = 8, CL_NPIX = CL_TW * CL_TH;
+constexpr int CL_THREADS = 2 * CL_NPIX;  // 8 pixel warps + 8 channel warps
+constexpr int CL_R = 24;                 // an item displaced farther than this from the tile's anchor is SLOW
+constexpr int CL_ROWS = 64;              // source-row window of a direction (CL_TH + 2 CL_R + 2 = 58 used), 2 rows per lane
+constexpr int CL_ZPAD = 4;               // dummy cells in front of every plane: the target of items without a tap
+constexpr int CL_SLOTS = 6;              // footprint cells per thread of a flush half (128 threads): <= 768 cells per direction
+constexpr int CL_MAXC = 31;              // channels (lanes 0 .. C-1; lane C counts the taps per footprint cell)
+constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the staged grad_out tile (odd)
+#ifndef CL_CB_N
+#define CL_CB_N 1
+#endif
+constexpr int CL_CB = CL_CB_N;                 // channels per batch of texture fetches in kernel 2
+
+struct ClChan {  // per flattened channel (groups that have a grad_out)
+  float* gs[2];  // grad_src plane of (n, t, c) per direction, or NULL
+  int g, c;
+  int pad_[2];
+};
+struct ClTex {  // per flattened channel: where kernel 2 finds the source plane
+  unsigned long long tex[2];  // texture object per direction
+  float row[2];               // first texture row of the plane
+  int pad_[2];
+};
+
+struct ClTab {  // footprint of one direction: row r is source row ybase + r, columns [rowx, rowx + len) at word rowbase of a plane
+  int xlo[CL_ROWS], xhi[CL_ROWS];
+  int rowx[CL_ROWS], rowbase[CL_ROWS], rowoff[CL_ROWS];
+  unsigned akey;
+  int cells, ybase, ok;
+};
+
+__device__ __forceinline__ void cl_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(CL_NPIX) : "memory"); }
+__device__ __forceinline__ void cl_red_s32(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void cl_red_s32_4(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0+4], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// one warp: segment lengths and placement of one direction's rows.  A pixel recorded [x0, x0+1] on its nw row only; its sw / se
+// taps are the same columns one row down, so the segment of row r is own[r] U own[r-1].
+__device__ __forceinline__ void cl_tab_scan(ClTab& tb, int max_cells) {
+  const int lane = threadIdx.x & 31;
+  int olo[2], ohi[2], xs[2], ln[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    olo[h] = tb.xlo[2 * lane + h];
+    ohi[h] = tb.xhi[2 * lane + h];
+  }
+  int plo = __shfl_up_sync(0xffffffffu, olo[1], 1), phi = __shfl_up_sync(0xffffffffu, ohi[1], 1);
+  if (lane == 0) plo = 0x7fffffff, phi = -0x7fffffff;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int lo = min(olo[h], h == 0 ? plo : olo[0]), hi = max(ohi[h], h == 0 ? phi : ohi[0]);
+    const bool has = lo <= hi;
+    xs[h] = has ? lo : 0;
+    ln[h] = has ? hi - lo + 1 : 0;
+  }
+  const int mine = ln[0] + ln[1];
+  int v = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
+  }
+  int run = v - mine;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = 2 * lane + h;
+    tb.rowx[r] = xs[h];
+    tb.rowoff[r] = run;
+    tb.rowbase[r] = CL_ZPAD + run;
+    run += ln[h];
+  }
+  if (lane == 31) {
+    tb.cells = run;
+    tb.ok = run <= max_cells;
+  }
+}
+
+// one SLOW item (pixel, direction) or the items of non-finite channels: exact float atomics to global memory, lane = channel
+template <int NDIRS>
+__device__ __forceinline__ void cl_exact_item(const Params& P, const GradP& Q, const ClChan* chan, const float* gos, int Cn, int n,
+                                              int t, int i, int j, int pp, int d, bool lane_on) {
+  const int lane = threadIdx.x & 31;
+  Tap k;
+  compute_tap(P.geo, P.dir[d], n, t, i, j, k);
+  if (lane < Cn && lane_on) {
+    const float g = gos[lane * CL_GS + pp];
+    scatter_atomic_px(Q, chan[lane].g, d, n, t, chan[lane].c, k, P.dir[d].blend ? g * k.blend : g);
+  }
+}
+
+// flush of `np` planes (every second plane of a group): thread <-> footprint cells htid + s * 128, s < NSL (consecutive lanes =
+// consecutive cells of a source row: coalesced RED.F32).  raw + cmb = sum of the fixed-point contributions of the cell (see the
+// scatter), * Sinv = float.  Cells outside the image / without a tap add an exact 0 at a clamped address; only the last slot
+// (ragged: cells past the end of the footprint) is predicated.
+template <int NSL>
+__device__ __forceinline__ void cl_flush_planes(float* gsp, long long gstep, int np, const float* sinv, unsigned ap, unsigned ap_step,
+                                                const int* goff, const int* cmb, bool last_on) {
+  float* p[NSL];
+#pragma unroll
+  for (int s = 0; s < NSL; ++s) p[s] = gsp + goff[s];
+#pragma unroll 1
+  for (int q = 0; q < np; ++q) {
+    const float Sinv = sinv[2 * q];
+#pragma unroll
+    for (int s = 0; s < NSL; ++s) {
+      if (s < NSL - 1 || last_on) {
+        int raw;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ap + (unsigned)(s * (CL_NPIX / 2) * 4)));
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p[s]), "f"((float)(raw + cmb[s]) * Sinv) : "memory");
+      }
+      p[s] += gstep;
+    }
+    ap += ap_step;
+  }
+}
+
+template <int NDIRS, bool ALIGN, bool BORDER>
+__global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
+                                                               const __grid_constant__ TexP X, int acc_words) {
+  extern __shared__ float4 cl_smem4[];
+  __shared__ ClTab tab[NDIRS];
+  __shared__ __align__(16) ClChan chan[CL_MAXC];
+  __shared__ __align__(16) ClTex ctex[CL_MAXC];
+  __shared__ __align__(16) float4 wq[NDIRS * CL_NPIX];  // item (p, d) at d * 256 + p: bilinear weights * blend
+  __shared__ __align__(8) uint2 oo[NDIRS * CL_NPIX];    //                           byte offsets of the nw / sw taps inside a plane
+  __shared__ unsigned amax_s[32];
+  __shared__ float sinv_s[32];
+  __shared__ float zeros_s[32];
+  __shared__ unsigned short slow_s[NDIRS * CL_NPIX];  // (p << 1) | d
+  __shared__ unsigned blmax_s;
+  __shared__ int nslow_s;
+  __shared__ unsigned gsmask_s[2];  // per direction: channels (bits) that have a grad_src plane
+
+  const Geo& G = P.geo;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool pixrole = warp < 8;
+  const int pw = warp & 7, pp = (pw << 5) | lane;  // the pixel this thread owns (pixel role) / stages (channel role)
+  const int j = blockIdx.x * CL_TW + (pw & 3) * 8 + (lane & 7);
+  const int i = blockIdx.y * CL_TH + (pw >> 2) * 4 + (lane >> 3);
+  const int i0 = blockIdx.y * CL_TH;
+  int n, t;
+  if (G.T == 1) {
+    n = blockIdx.z;
+    t = 0;
+  } else {
+    n = blockIdx.z / G.T;
+    t = blockIdx.z - n * G.T;
+  }
+  const bool inimg = j < G.W && i < G.H;
+  const int ic = min(i, G.H - 1), jc = min(j, G.W - 1);  // ragged tiles: clamped address, results masked
+  float* const gos = reinterpret_cast<float*>(cl_smem4);
+  int Cn = 0;  // flattened channels of the groups that have a grad_out (host-checked: 1 .. CL_MAXC)
+  for (int g = 0; g < G.n_groups; ++g)
+    if (Q.grad_out[g]) Cn += P.grp[g].C;
+
+  if (pixrole) {
+    // ------------------------------------------------------------------ phase A, pixel role: taps, tables, descriptors
+    float tx[NDIRS], ty[NDIRS], ux[NDIRS], uy[NDIRS], bl[NDIRS], fx1[NDIRS], fy1[NDIRS];
+    unsigned vld[NDIRS], clip = 0u;
+    int x0[NDIRS], y0[NDIRS];
+    {
+      // all global loads first: one exposed memory latency
+      float lfx[NDIRS], lfy[NDIRS], lgt[NDIRS], lbl[NDIRS];
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const DirP& D = P.dir[d];
+        const DirAt at = dir_at(D, n, t);
+        const int of = ic * (int)D.flow_sh + jc;
+        lfx[d] = __ldg(at.flow + of);
+        lfy[d] = __ldg(at.flow + D.flow_sc + of);
+        lgt[d] = at.gate ? __ldg(at.gate + (ic * (int)D.gate_sh + jc)) : 1.0f;
+        lbl[d] = at.blend ? __ldg(at.blend + (ic * (int)D.blend_sh + jc)) : 1.0f;
+      }
+      for (int q = tid; q < NDIRS * CL_ROWS; q += CL_NPIX) {
+        ClTab& T = tab[(NDIRS > 1 && q >= CL_ROWS) ? 1 : 0];
+        const int r = q >= CL_ROWS ? q - CL_ROWS : q;
+        T.xlo[r] = 0x7fffffff;
+        T.xhi[r] = -0x7fffffff;
+      }
+      if (tid < NDIRS) tab[tid].akey = 0xffffffffu;
+      if (tid == 0) {
+        nslow_s = 0;
+        blmax_s = 0u;
+      }
+      const float bx = base_coord(jc, G.W, G.stepx), by = base_coord(ic, G.H, G.stepy);
+      const float fW = (float)G.W, fW1 = (float)(G.W - 1), fH = (float)G.H, fH1 = (float)(G.H - 1);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {  // the arithmetic of compute_tap (fwb_coords.cuh), bit for bit
+        const DirP& D = P.dir[d];
+        float fx = lfx[d], fy = lfy[d];
+        if (D.gate != nullptr) {
+          fx = __fmul_rn(fx, lgt[d]);
+          fy = __fmul_rn(fy, lgt[d]);
+        }
+        bl[d] = lbl[d];
+        const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by);
+        const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1), iy = source_index_fast<ALIGN, BORDER>(gy, fH, fH1);
+        if (BORDER) {  // clipped <=> the unclipped coordinate was <= 0 or >= size-1: the coordinate gradient is zero there
+          const float cx_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), fW1) : __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), fW, -1.0f), 0.5f);
+          const float cy_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), fH1) : __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), fH, -1.0f), 0.5f);
+          clip |= ((unsigned)(cx_ <= 0.f || cx_ >= fW1) | ((unsigned)(cy_ <= 0.f || cy_ >= fH1) << 1)) << (2 * d);
+        }
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        x0[d] = (int)fx0;
+        y0[d] = (int)fy0;
+        tx[d] = __fsub_rn(ix, fx0);
+        ty[d] = __fsub_rn(iy, fy0);
+        ux[d] = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+        uy[d] = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
+        const bool xin0 = (unsigned)x0[d] < (unsigned)G.W, xin1 = (unsigned)(x0[d] + 1) < (unsigned)G.W;
+        const bool yin0 = (unsigned)y0[d] < (unsigned)G.H, yin1 = (unsigned)(y0[d] + 1) < (unsigned)G.H;
+        vld[d] = inimg ? ((unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
+                          ((unsigned)(xin1 && yin1) << 3))
+                       : 0u;
+        fx1[d] = vld[d] ? (float)(x0[d] + 1) : 0.0f;
+        fy1[d] = vld[d] ? (float)(y0[d] + 1) : 0.0f;
+      }
+    }
+    cl_bar(1);
+    float blm = 0.f;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      if (inimg) blm = __uint_as_float(max(__float_as_uint(blm), __float_as_uint(P.dir[d].blend ? fabsf(bl[d]) : 1.0f)));
+      // anchor vote: the displacement (x0 - j, y0 - i) of the tile's least displaced item, as one 32-bit key
+      const int dx = min(max(x0[d] - j, -1024), 1023), dy = min(max(y0[d] - i, -1024), 1023);
+      const unsigned mag = (unsigned)min(abs(dx) + abs(dy), 1023);
+      const unsigned key = vld[d] ? ((mag << 22) | (((unsigned)dx & 0x7ffu) << 11) | ((unsigned)dy & 0x7ffu)) : 0xffffffffu;
+      const unsigned best = __reduce_min_sync(0xffffffffu, key);
+      if (lane == 0 && best != 0xffffffffu) atomicMin(&tab[d].akey, best);
+    }
+    {
+      const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(blm));  // NaN wins (bit patterns of non-negative floats)
+      if (lane == 0 && mb != 0u) atomicMax(&blmax_s, mb);
+    }
+    cl_bar(1);
+    bool fast[NDIRS], slow[NDIRS];
+    int rr[NDIRS];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      const unsigned ak = tab[d].akey;  // ~0 when no item of the tile has a tap
+      const int adx = ((int)(ak << 10)) >> 21, ady = ((int)(ak << 21)) >> 21;
+      const bool far = abs(x0[d] - j - adx) > CL_R || abs(y0[d] - i - ady) > CL_R;
+      fast[d] = vld[d] != 0u && !far;
+      slow[d] = vld[d] != 0u && far;
+      rr[d] = y0[d] - (i0 + ady - CL_R);  // 0 .. CL_TH + 2 CL_R - 1 for fast items
+      if (tid == 0) tab[d].ybase = i0 + ady - CL_R;
+      if (fast[d]) {
+        atomicMin(&tab[d].xlo[rr[d]], x0[d]);
+        atomicMax(&tab[d].xhi[rr[d]], x0[d] + 1);
+      }
+    }
+    cl_bar(1);
+    if (warp == 0) {
+      const int cmax = min(acc_words / (Cn + 1) - CL_ZPAD - 1, CL_SLOTS * (CL_NPIX / 2));
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) cl_tab_scan(tab[d], cmax);
+    }
+    cl_bar(1);
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      const ClTab& T = tab[d];
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint2 o = make_uint2(0u, 0u);
+      if (fast[d] && T.ok) {
+        const float b = P.dir[d].blend ? bl[d] : 1.0f;
+        const float wl = b * ux[d], wr = b * tx[d];
+        w = make_float4(wl * uy[d], wr * uy[d], wl * ty[d], wr * ty[d]);
+        // taps outside the image (zeros padding) add nothing: their footprint cells only ever receive zeros
+        if (!(vld[d] & 1u)) w.x = 0.f;
+        if (!(vld[d] & 2u)) w.y = 0.f;
+        if (!(vld[d] & 4u)) w.z = 0.f;
+        if (!(vld[d] & 8u)) w.w = 0.f;
+        o.x = 4u * (unsigned)(T.rowbase[rr[d]] + (x0[d] - T.rowx[rr[d]]));
+        o.y = 4u * (unsigned)(T.rowbase[rr[d] + 1] + (x0[d] - T.rowx[rr[d] + 1]));
+      } else if (slow[d] || fast[d]) {
+        slow_s[atomicAdd(&nslow_s, 1)] = (unsigned short)((pp << 1) | d);
+      }
+      wq[d * CL_NPIX + pp] = w;
+      oo[d * CL_NPIX + pp] = o;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase B, pixel role: kernel 2 on the texture units
+    // gix = sum_c gw_c [uy (b_c - a_c) + ty (d_c - c_c)] etc. (ATen grid_sampler_2d_backward): the weights do not depend on the
+    // channel, so only the four sums  A_k = sum_c grad_out_c * tap_k,c  are accumulated per (pixel, direction) - one TLD4 and
+    // four FFMA per channel - and the weights are applied once at the end.  The fetches run one batch ahead of the sums.
+    float A[NDIRS][4];
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) A[d][0] = A[d][1] = A[d][2] = A[d][3] = 0.0f;
+    bool part = false;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) part |= vld[d] != 15u;
+    const bool masked = __any_sync(0xffffffffu, part);  // some tap of this warp is outside the image (borders, ragged tiles)
+    const float fH = (float)G.H;
+    const float* gq = gos + pp;
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const int C = P.grp[g].C;
+      unsigned long long th[NDIRS];
+      float row0[NDIRS];
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const TexSrc& S = X.s[g][d];
+        const int blk = n / S.nb;
+        th[d] = S.tex[blk];
+        row0[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+      }
+      const float lastc = (float)(C - 1);
+      auto fetchb = [&](int b, float4 (*q)[NDIRS]) {
+#pragma unroll
+        for (int u = 0; u < CL_CB; ++u) {
+          const float cr = fminf((float)(b * CL_CB + u), lastc) * fH;  // past the end: the last plane again (its grad_out counts as 0)
+#pragma unroll
+          for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row0[d] + cr, 0);
+        }
+      };
+      auto consume = [&](int b, const float4 (*q)[NDIRS]) {
+#pragma unroll
+        for (int u = 0; u < CL_CB; ++u) {
+          const int c = b * CL_CB + u;
+          const float gv = c < C ? gq[c * CL_GS] : 0.0f;
+#pragma unroll
+          for (int d = 0; d < NDIRS; ++d) {
+            // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
+            if (masked) {
+              const unsigned v = vld[d];
+              A[d][0] = fmaf(gv, (v & 1u) ? q[u][d].w : 0.0f, A[d][0]);
+              A[d][1] = fmaf(gv, (v & 2u) ? q[u][d].z : 0.0f, A[d][1]);
+              A[d][2] = fmaf(gv, (v & 4u) ? q[u][d].x : 0.0f, A[d][2]);
+              A[d][3] = fmaf(gv, (v & 8u) ? q[u][d].y : 0.0f, A[d][3]);
+            } else {
+              A[d][0] = fmaf(gv, q[u][d].w, A[d][0]);
+              A[d][1] = fmaf(gv, q[u][d].z, A[d][1]);
+              A[d][2] = fmaf(gv, q[u][d].x, A[d][2]);
+              A[d][3] = fmaf(gv, q[u][d].y, A[d][3]);
+            }
+          }
+        }
+      };
+      const int nb = (C + CL_CB - 1) / CL_CB;
+      float4 qa[CL_CB][NDIRS], qb[CL_CB][NDIRS];
+      fetchb(0, qa);
+#pragma unroll 1
+      for (int b = 0; b < nb; b += 2) {
+        if (b + 1 < nb) fetchb(b + 1, qb);
+        consume(b, qa);
+        if (b + 2 < nb) fetchb(b + 2, qa);
+        if (b + 1 < nb) consume(b + 1, qb);
+      }
+      gq += C * CL_GS;
+    }
+    if (inimg) {
+      // coordinate gradient -> grad_flow / grad_gate / grad_blend.  The multipliers are d(ix)/d(gx) = W/2 or (W-1)/2, zero where
+      // border padding clipped the coordinate; the raw flow and the gate are reloaded only when there is a gate.
+      const float mxc = ALIGN ? __fmul_rn((float)(G.W - 1), 0.5f) : __fmul_rn((float)G.W, 0.5f);
+      const float myc = ALIGN ? __fmul_rn((float)(G.H - 1), 0.5f) : __fmul_rn((float)G.H, 0.5f);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const float a = A[d][0], b = A[d][1], cc = A[d][2], dd = A[d][3];
+        float gbl = 0.0f, sc = 1.0f;
+        if (P.dir[d].blend != nullptr) {
+          const float top = fmaf(b, tx[d], a * ux[d]), bot = fmaf(dd, tx[d], cc * ux[d]);
+          gbl = fmaf(bot, ty[d], top * uy[d]);
+          sc = bl[d];
+        }
+        const float gix = sc * fmaf(ty[d], dd - cc, uy[d] * (b - a));
+        const float giy = sc * fmaf(tx[d], dd - b, ux[d] * (cc - a));
+        const unsigned cb = clip >> (2 * d);
+        Tap k;
+        k.mx = (cb & 1u) ? 0.f : mxc;
+        k.my = (cb & 2u) ? 0.f : myc;
+        k.fx = k.fy = 0.f;
+        k.gate = 1.f;
+        const DirP& D = P.dir[d];
+        if (D.gate != nullptr) {
+          const DirAt at = dir_at(D, n, t);
+          const int of = i * (int)D.flow_sh + j;
+          k.fx = __ldg(at.flow + of);
+          k.fy = __ldg(at.flow + D.flow_sc + of);
+          k.gate = __ldg(at.gate + (i * (int)D.gate_sh + j));
+        }
+        bwdflow_store(P, Q, d, n, t, i, j, k, gix, giy, gbl);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- phase A, channel role: grad_out tile -> shared memory
+  if (warp == 8) {  // channel tables over the groups that have a grad_out (the others contribute nothing)
+    int base = 0;
+    unsigned m0 = 0u, m1 = 0u;
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const int C = P.grp[g].C;
+      ClChan e;
+      ClTex x;
+      e.g = g;
+      e.c = lane;
+      e.pad_[0] = e.pad_[1] = x.pad_[0] = x.pad_[1] = 0;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        float* gs = (d < NDIRS && lane < C) ? Q.grad_src[g][d] : nullptr;
+        e.gs[d] = gs ? gs + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)lane * Q.gs_sc[g][d] : nullptr;
+        x.tex[d] = 0ull;
+        x.row[d] = 0.0f;
+        if (d < NDIRS) {
+          const TexSrc& S = X.s[g][d];
+          const int blk = n / S.nb;
+          x.tex[d] = S.tex[blk];
+          x.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t + lane * G.H);
+        }
+      }
+      if (lane < C) {
+        chan[base + lane] = e;
+        ctex[base + lane] = x;
+      }
+      m0 |= __ballot_sync(0xffffffffu, e.gs[0] != nullptr) << base;
+      m1 |= __ballot_sync(0xffffffffu, e.gs[1] != nullptr) << base;
+      base += C;
+    }
+    amax_s[lane] = 0u;
+    zeros_s[lane] = 0.0f;
+    if (lane == 0) {
+      gsmask_s[0] = m0;
+      gsmask_s[1] = m1;
+    }
+  }
+  {
+    // out-of-image pixels of ragged tiles stage the value of the clamped address: their items carry zero weights
+    float* gd = gos + pp;
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const float* gp = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
+      const int C = P.grp[g].C;
+      const long long sc = Q.go_sc[g];
+      int c = 0;
+      for (; c + 4 <= C; c += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = __ldcs(gp);
+          gp += sc;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gd[u * CL_GS] = v[u];
+        gd += 4 * CL_GS;
+      }
+      for (; c < C; ++c) {
+        *gd = __ldcs(gp);
+        gp += sc;
+        gd += CL_GS;
+      }
+    }
+  }
+  __syncthreads();
+
+  // -------------------------------------------------------------------- phase B, channel role: scatter + flush
+  const int ctid = tid - CL_NPIX;
+  int* const acc = reinterpret_cast<int*>(gos + ((Cn * CL_GS + 3) & ~3));
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
+  constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: fma(x, y, MAGIC) holds round-to-nearest(x*y) in its low mantissa bits
+  constexpr int MAGIC_BITS = 0x4B400000;
+  const float* gl = gos + (lane < Cn ? lane : 0) * CL_GS + (pw << 5);
+  if (lane < Cn) {  // max |grad_out| of this lane's channel over the warp's 32 pixels; NaN wins (integer compare of the magnitudes)
+    unsigned m = 0u;
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) m = max(m, __float_as_uint(gl[u]) & 0x7fffffffu);
+    if (m != 0u) atomicMax(&amax_s[lane], m);
+  }
+  cl_bar(2);
+  // scale of this lane's channel
+  float S = 0.f;
+  bool finite = true;
+  if (lane < Cn) {
+    const unsigned ab = amax_s[lane], bb = blmax_s;
+    const float prod = __uint_as_float(ab) * __uint_as_float(bb);
+    const unsigned pb = __float_as_uint(prod);
+    finite = ab < 0x7f800000u && bb < 0x7f800000u && pb < 0x7f800000u;
+    const int sexp = min(252, max(2, 274 - (int)(pb >> 23)));  // biased exponent of 2^(20 - exponent(amax))
+    if (finite && pb != 0u) S = __uint_as_float((unsigned)sexp << 23);
+    if (warp == 8) sinv_s[lane] = (finite && pb != 0u) ? __uint_as_float((unsigned)(254 - sexp) << 23) : 0.f;
+  }
+  const bool any_nonfinite = __any_sync(0xffffffffu, !finite);
+  if (lane >= Cn || !finite) gl = zeros_s;  // the tap counter lane and non-finite channels put in exact zeros
+  // lane Cn counts the taps per cell: fma(0, w, denorm_min) has the bit pattern 1
+  const float magic = lane == Cn ? __int_as_float(1) : MAGIC;
+#pragma unroll 1
+  for (int d = 0; d < NDIRS; ++d) {
+    const ClTab& T = tab[d];
+    const unsigned gsm = gsmask_s[d];
+    if (!T.ok || T.cells == 0 || gsm == 0u) continue;  // (uniform) nothing to scatter in this direction
+    const int PS = (CL_ZPAD + T.cells) | 1;
+    {  // clear the planes (and the tap counter plane)
+      const int n4 = ((Cn + 1) * PS + 3) >> 2;
+      for (int q = ctid; q < n4; q += CL_NPIX) asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + 16u * (unsigned)q), "r"(0) : "memory");
+    }
+    cl_bar(2);
+    if (lane <= Cn) {
+      // every tap adds the raw bits of fma(g * S, w, MAGIC) = MAGIC_BITS + k (k = the rounded fixed-point product); a cell hit
+      // by cnt taps then holds cnt * MAGIC_BITS + sum k (mod 2^32): the flush takes cnt * MAGIC_BITS off again
+      const float Sd = ((gsm >> lane) & 1u) ? S : 0.f;
+      const unsigned la = acc_s + 4u * (unsigned)(lane * PS);
+      const float4* wd = wq + d * CL_NPIX + (pw << 5);
+      const uint2* od = oo + d * CL_NPIX + (pw << 5);
+#pragma unroll 4
+      for (int u = 0; u < 32; ++u) {
+        const float gsv = gl[u] * Sd;
+        const float4 w = wd[u];
+        const uint2 o = od[u];
+        const unsigned a0 = la + o.x, a1 = la + o.y;
+        cl_red_s32(a0, __float_as_int(fmaf(gsv, w.x, magic)));
+        cl_red_s32_4(a0, __float_as_int(fmaf(gsv, w.y, magic)));
+        cl_red_s32(a1, __float_as_int(fmaf(gsv, w.z, magic)));
+        cl_red_s32_4(a1, __float_as_int(fmaf(gsv, w.w, magic)));
+      }
+    }
+    cl_bar(2);
+    int gsh = 0;
+    for (int g = G.n_groups - 1; g >= 0; --g)
+      if (Q.grad_out[g] && Q.grad_src[g][d]) gsh = Q.gs_sh[g][d];  // all groups agree (host-checked)
+    // two halves of 128 threads, half h takes the planes cf = h, h + 2, ...
+    const int half = ctid >> 7, htid = ctid & 127;
+    const int nsl = (T.cells + CL_NPIX / 2 - 1) / (CL_NPIX / 2);
+    int goff[CL_SLOTS], cmb[CL_SLOTS];
+    bool last_on = false;
+#pragma unroll
+    for (int s = 0; s < CL_SLOTS; ++s) {
+      goff[s] = 0;
+      cmb[s] = 0;
+      if (s < nsl) {
+        const int kk = htid + s * (CL_NPIX / 2);
+        if (kk < T.cells) {
+          int r = 0;  // last row with rowoff[r] <= kk
+#pragma unroll
+          for (int step = CL_ROWS / 2; step > 0; step >>= 1)
+            if (T.rowoff[r + step] <= kk) r += step;
+          const int y = T.ybase + r, col = T.rowx[r] + (kk - T.rowoff[r]);
+          const int cnt = acc[Cn * PS + CL_ZPAD + kk];
+          // a cell outside the image only ever received zeros (weights masked): it adds 0.0 at the clamped address
+          goff[s] = min(max(y, 0), G.H - 1) * gsh + min(max(col, 0), G.W - 1);
+          cmb[s] = -cnt * MAGIC_BITS;
+          if (s == nsl - 1) last_on = true;
+        }
+      }
+    }
+    const unsigned ps_b = 4u * (unsigned)PS;
+    const unsigned ap0 = acc_s + 4u * (unsigned)(CL_ZPAD + htid);
+    int cf = 0;
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const int C = P.grp[g].C;
+      if (Q.grad_src[g][d]) {
+        const int c0 = (half ^ cf) & 1;  // first channel of this group whose flattened index has this half's parity
+        const int np = (C - c0 + 1) >> 1;
+        const long long gsc = Q.gs_sc[g][d];
+        float* gsp = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + c0 * gsc;
+        const unsigned ap = ap0 + ps_b * (unsigned)(cf + c0);
+        const float* si = sinv_s + cf + c0;
+        switch (nsl) {
+          case 1: cl_flush_planes<1>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+          case 2: cl_flush_planes<2>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+          case 3: cl_flush_planes<3>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+          case 4: cl_flush_planes<4>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+          case 5: cl_flush_planes<5>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+          default: cl_flush_planes<6>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        }
+      }
+      cf += C;
+    }
+    if (d + 1 < NDIRS) cl_bar(2);  // the planes are reused by the next direction
+  }
+  // SLOW items, and every item of a non-finite channel: exact float atomics, lane = channel
+  const int nslow = nslow_s;
+  for (int q = pw; q < nslow; q += 8) {
+    const int e = slow_s[q], sp = e >> 1, sd = e & 1;
+    const int sw = sp >> 5, sl = sp & 31;
+    const int sj = blockIdx.x * CL_TW + (sw & 3) * 8 + (sl & 7), si = blockIdx.y * CL_TH + (sw >> 2) * 4 + (sl >> 3);
+    cl_exact_item<NDIRS>(P, Q, chan, gos, Cn, n, t, si, sj, sp, sd, true);
+  }
+  if (any_nonfinite) {
+    for (int u = 0; u < 32; ++u) {
+      const int sp = (pw << 5) | u;
+      const int sj = blockIdx.x * CL_TW + (pw & 3) * 8 + (u & 7), si = blockIdx.y * CL_TH + (pw >> 2) * 4 + (u >> 3);
+      for (int d = 0; d < NDIRS; ++d)
+        if (oo[d * CL_NPIX + sp].x != 0u) cl_exact_item<NDIRS>(P, Q, chan, gos, Cn, n, t, si, sj, sp, d, !finite);
+    }
+  }
+}
+
+}  // namespace fwb
