@@ -36,16 +36,18 @@ constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the st
 #ifndef CL_CB_N
 #define CL_CB_N 1
 #endif
+#ifndef CL_DBG
+#define CL_DBG 0  // 1: the pixel role returns at once, 2: the channel role returns at once (timing experiments)
+#endif
+#ifndef CL_REGS_K2
+#define CL_REGS_K2 0  // setmaxnreg of the pixel-role warps (0: leave the launch value)
+#define CL_REGS_K3 0
+#endif
 constexpr int CL_CB = CL_CB_N;                 // channels per batch of texture fetches in kernel 2
 
 struct ClChan {  // per flattened channel (groups that have a grad_out)
   float* gs[2];  // grad_src plane of (n, t, c) per direction, or NULL
   int g, c;
-  int pad_[2];
-};
-struct ClTex {  // per flattened channel: where kernel 2 finds the source plane
-  unsigned long long tex[2];  // texture object per direction
-  float row[2];               // first texture row of the plane
   int pad_[2];
 };
 
@@ -121,6 +123,9 @@ __device__ __forceinline__ void cl_exact_item(const Params& P, const GradP& Q, c
 template <int NSL>
 __device__ __forceinline__ void cl_flush_planes(float* gsp, long long gstep, int np, const float* sinv, unsigned ap, unsigned ap_step,
                                                 const int* goff, const int* cmb, bool last_on) {
+  // (opaque copies: keep the strides in registers instead of re-deriving them from the kernel parameters in the loop)
+  asm volatile("" : "+l"(gstep));
+  asm volatile("" : "+r"(ap_step));
   float* p[NSL];
 #pragma unroll
   for (int s = 0; s < NSL; ++s) p[s] = gsp + goff[s];
@@ -140,27 +145,107 @@ __device__ __forceinline__ void cl_flush_planes(float* gsp, long long gstep, int
   }
 }
 
+// everything channel independent about one pixel: the arithmetic of compute_tap (fwb_coords.cuh), bit for bit
+template <int NDIRS>
+struct ClTaps {
+  float tx[NDIRS], ty[NDIRS], ux[NDIRS], uy[NDIRS], bl[NDIRS];
+  int x0[NDIRS], y0[NDIRS];
+  unsigned vld[NDIRS];
+  unsigned clip;  // 2 bits per direction: border padding clipped ix / iy (the coordinate gradient is then zero)
+};
+template <int NDIRS, bool ALIGN, bool BORDER>
+__device__ __forceinline__ void cl_taps(const Params& P, int n, int t, int ic, int jc, bool inimg, ClTaps<NDIRS>& k) {
+  const Geo& G = P.geo;
+  float lfx[NDIRS], lfy[NDIRS], lgt[NDIRS], lbl[NDIRS];  // all global loads first: one exposed memory latency
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const DirP& D = P.dir[d];
+    const DirAt at = dir_at(D, n, t);
+    const int of = ic * (int)D.flow_sh + jc;
+    lfx[d] = __ldg(at.flow + of);
+    lfy[d] = __ldg(at.flow + D.flow_sc + of);
+    lgt[d] = at.gate ? __ldg(at.gate + (ic * (int)D.gate_sh + jc)) : 1.0f;
+    lbl[d] = at.blend ? __ldg(at.blend + (ic * (int)D.blend_sh + jc)) : 1.0f;
+  }
+  const float bx = base_coord(jc, G.W, G.stepx), by = base_coord(ic, G.H, G.stepy);
+  const float fW = (float)G.W, fW1 = (float)(G.W - 1), fH = (float)G.H, fH1 = (float)(G.H - 1);
+  k.clip = 0u;
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    const DirP& D = P.dir[d];
+    float fx = lfx[d], fy = lfy[d];
+    if (D.gate != nullptr) {
+      fx = __fmul_rn(fx, lgt[d]);
+      fy = __fmul_rn(fy, lgt[d]);
+    }
+    k.bl[d] = lbl[d];
+    const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by);
+    const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1), iy = source_index_fast<ALIGN, BORDER>(gy, fH, fH1);
+    if (BORDER) {  // clipped <=> the unclipped coordinate was <= 0 or >= size-1
+      const float cx_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), fW1) : __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), fW, -1.0f), 0.5f);
+      const float cy_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), fH1) : __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), fH, -1.0f), 0.5f);
+      k.clip |= ((unsigned)(cx_ <= 0.f || cx_ >= fW1) | ((unsigned)(cy_ <= 0.f || cy_ >= fH1) << 1)) << (2 * d);
+    }
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    k.x0[d] = (int)fx0;
+    k.y0[d] = (int)fy0;
+    k.tx[d] = __fsub_rn(ix, fx0);
+    k.ty[d] = __fsub_rn(iy, fy0);
+    k.ux[d] = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+    k.uy[d] = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
+    const bool xin0 = (unsigned)k.x0[d] < (unsigned)G.W, xin1 = (unsigned)(k.x0[d] + 1) < (unsigned)G.W;
+    const bool yin0 = (unsigned)k.y0[d] < (unsigned)G.H, yin1 = (unsigned)(k.y0[d] + 1) < (unsigned)G.H;
+    k.vld[d] = inimg ? ((unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
+                        ((unsigned)(xin1 && yin1) << 3))
+                     : 0u;
+  }
+}
+
+struct ClSlow {  // a SLOW item with its taps: float atomics straight to global memory
+  float w[4];   // bilinear weights * blend
+  int goff;     // y0 * row stride + x0 inside a grad_src plane
+  int key;      // pixel << 8 | direction << 4 | validity bits
+};
+constexpr int CL_SLOWCAP = 96;
+
+// grad_src[tap] += w_tap * g for the 4 taps of one item in one plane (ATen grid_sampler_2d_backward's atomicAdd scatter); the
+// (x0, x0+1) pair of a row goes out as one 8-byte vector reduction when both taps are inside the image and the pair is aligned
+__device__ __forceinline__ void cl_scatter_exact(float* gs, int sh, unsigned vld, const float* w, float g) {
+  const int off[4] = {0, 1, sh, sh + 1};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float* p0 = gs + off[2 * r];
+    const unsigned vv = (vld >> (2 * r)) & 3u;
+    if (vv == 3u && (reinterpret_cast<uintptr_t>(p0) & 7u) == 0u) {
+      red_add_v2(p0, w[2 * r] * g, w[2 * r + 1] * g);
+    } else {
+#pragma unroll
+      for (int q = 2 * r; q < 2 * r + 2; ++q)
+        if (vld & (1u << q)) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gs + off[q]), "f"(w[q] * g) : "memory");
+    }
+  }
+}
+
 template <int NDIRS, bool ALIGN, bool BORDER>
 __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
                                                                const __grid_constant__ TexP X, int acc_words) {
   extern __shared__ float4 cl_smem4[];
   __shared__ ClTab tab[NDIRS];
   __shared__ __align__(16) ClChan chan[CL_MAXC];
-  __shared__ __align__(16) ClTex ctex[CL_MAXC];
   __shared__ __align__(16) float4 wq[NDIRS * CL_NPIX];  // item (p, d) at d * 256 + p: bilinear weights * blend
   __shared__ __align__(8) uint2 oo[NDIRS * CL_NPIX];    //                           byte offsets of the nw / sw taps inside a plane
+  __shared__ __align__(8) ClSlow slowtap[CL_SLOWCAP];
   __shared__ unsigned amax_s[32];
   __shared__ float sinv_s[32];
   __shared__ float zeros_s[32];
-  __shared__ unsigned short slow_s[NDIRS * CL_NPIX];  // (p << 1) | d
+  __shared__ unsigned short slow_s[NDIRS * CL_NPIX];  // (p << 1) | d: SLOW items beyond the capacity of slowtap
   __shared__ unsigned blmax_s;
   __shared__ int nslow_s;
   __shared__ unsigned gsmask_s[2];  // per direction: channels (bits) that have a grad_src plane
 
   const Geo& G = P.geo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool pixrole = warp < 8;
-  const int pw = warp & 7, pp = (pw << 5) | lane;  // the pixel this thread owns (pixel role) / stages (channel role)
+  const int pw = warp & 7, pp = (pw << 5) | lane;  // the pixel this thread owns
   const int j = blockIdx.x * CL_TW + (pw & 3) * 8 + (lane & 7);
   const int i = blockIdx.y * CL_TH + (pw >> 2) * 4 + (lane >> 3);
   const int i0 = blockIdx.y * CL_TH;
@@ -179,24 +264,16 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   for (int g = 0; g < G.n_groups; ++g)
     if (Q.grad_out[g]) Cn += P.grp[g].C;
 
-  if (pixrole) {
-    // ------------------------------------------------------------------ phase A, pixel role: taps, tables, descriptors
-    float tx[NDIRS], ty[NDIRS], ux[NDIRS], uy[NDIRS], bl[NDIRS], fx1[NDIRS], fy1[NDIRS];
-    unsigned vld[NDIRS], clip = 0u;
-    int x0[NDIRS], y0[NDIRS];
+  if (warp < 8) {
+    // ==================================================================== pixel role
+    if (CL_DBG & 1) return;
+#if CL_REGS_K2
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CL_REGS_K2));
+#endif
+    ClTaps<NDIRS> k;
+    cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic, jc, inimg, k);
     {
-      // all global loads first: one exposed memory latency
-      float lfx[NDIRS], lfy[NDIRS], lgt[NDIRS], lbl[NDIRS];
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        const DirP& D = P.dir[d];
-        const DirAt at = dir_at(D, n, t);
-        const int of = ic * (int)D.flow_sh + jc;
-        lfx[d] = __ldg(at.flow + of);
-        lfy[d] = __ldg(at.flow + D.flow_sc + of);
-        lgt[d] = at.gate ? __ldg(at.gate + (ic * (int)D.gate_sh + jc)) : 1.0f;
-        lbl[d] = at.blend ? __ldg(at.blend + (ic * (int)D.blend_sh + jc)) : 1.0f;
-      }
+      // ---- footprint tables and item descriptors of the scatter (thread = pixel; barrier 1 = the 8 pixel warps)
       for (int q = tid; q < NDIRS * CL_ROWS; q += CL_NPIX) {
         ClTab& T = tab[(NDIRS > 1 && q >= CL_ROWS) ? 1 : 0];
         const int r = q >= CL_ROWS ? q - CL_ROWS : q;
@@ -208,115 +285,104 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         nslow_s = 0;
         blmax_s = 0u;
       }
-      const float bx = base_coord(jc, G.W, G.stepx), by = base_coord(ic, G.H, G.stepy);
-      const float fW = (float)G.W, fW1 = (float)(G.W - 1), fH = (float)G.H, fH1 = (float)(G.H - 1);
+      int gsh[NDIRS];  // row stride of the grad_src planes per direction (all groups agree, host-checked)
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {  // the arithmetic of compute_tap (fwb_coords.cuh), bit for bit
-        const DirP& D = P.dir[d];
-        float fx = lfx[d], fy = lfy[d];
-        if (D.gate != nullptr) {
-          fx = __fmul_rn(fx, lgt[d]);
-          fy = __fmul_rn(fy, lgt[d]);
-        }
-        bl[d] = lbl[d];
-        const float gx = __fmaf_rn(D.sign, fx, bx), gy = __fmaf_rn(D.sign, fy, by);
-        const float ix = source_index_fast<ALIGN, BORDER>(gx, fW, fW1), iy = source_index_fast<ALIGN, BORDER>(gy, fH, fH1);
-        if (BORDER) {  // clipped <=> the unclipped coordinate was <= 0 or >= size-1: the coordinate gradient is zero there
-          const float cx_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), fW1) : __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), fW, -1.0f), 0.5f);
-          const float cy_ = ALIGN ? __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), fH1) : __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), fH, -1.0f), 0.5f);
-          clip |= ((unsigned)(cx_ <= 0.f || cx_ >= fW1) | ((unsigned)(cy_ <= 0.f || cy_ >= fH1) << 1)) << (2 * d);
-        }
-        const float fx0 = floorf(ix), fy0 = floorf(iy);
-        x0[d] = (int)fx0;
-        y0[d] = (int)fy0;
-        tx[d] = __fsub_rn(ix, fx0);
-        ty[d] = __fsub_rn(iy, fy0);
-        ux[d] = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
-        uy[d] = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
-        const bool xin0 = (unsigned)x0[d] < (unsigned)G.W, xin1 = (unsigned)(x0[d] + 1) < (unsigned)G.W;
-        const bool yin0 = (unsigned)y0[d] < (unsigned)G.H, yin1 = (unsigned)(y0[d] + 1) < (unsigned)G.H;
-        vld[d] = inimg ? ((unsigned)(xin0 && yin0) | ((unsigned)(xin1 && yin0) << 1) | ((unsigned)(xin0 && yin1) << 2) |
-                          ((unsigned)(xin1 && yin1) << 3))
-                       : 0u;
-        fx1[d] = vld[d] ? (float)(x0[d] + 1) : 0.0f;
-        fy1[d] = vld[d] ? (float)(y0[d] + 1) : 0.0f;
+      for (int d = 0; d < NDIRS; ++d) {
+        gsh[d] = 0;
+        for (int g = G.n_groups - 1; g >= 0; --g)
+          if (Q.grad_out[g] && Q.grad_src[g][d]) gsh[d] = Q.gs_sh[g][d];
       }
-    }
-    cl_bar(1);
-    float blm = 0.f;
+      cl_bar(1);
+      float blm = 0.f;
 #pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      if (inimg) blm = __uint_as_float(max(__float_as_uint(blm), __float_as_uint(P.dir[d].blend ? fabsf(bl[d]) : 1.0f)));
-      // anchor vote: the displacement (x0 - j, y0 - i) of the tile's least displaced item, as one 32-bit key
-      const int dx = min(max(x0[d] - j, -1024), 1023), dy = min(max(y0[d] - i, -1024), 1023);
-      const unsigned mag = (unsigned)min(abs(dx) + abs(dy), 1023);
-      const unsigned key = vld[d] ? ((mag << 22) | (((unsigned)dx & 0x7ffu) << 11) | ((unsigned)dy & 0x7ffu)) : 0xffffffffu;
-      const unsigned best = __reduce_min_sync(0xffffffffu, key);
-      if (lane == 0 && best != 0xffffffffu) atomicMin(&tab[d].akey, best);
-    }
-    {
-      const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(blm));  // NaN wins (bit patterns of non-negative floats)
-      if (lane == 0 && mb != 0u) atomicMax(&blmax_s, mb);
-    }
-    cl_bar(1);
-    bool fast[NDIRS], slow[NDIRS];
-    int rr[NDIRS];
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      const unsigned ak = tab[d].akey;  // ~0 when no item of the tile has a tap
-      const int adx = ((int)(ak << 10)) >> 21, ady = ((int)(ak << 21)) >> 21;
-      const bool far = abs(x0[d] - j - adx) > CL_R || abs(y0[d] - i - ady) > CL_R;
-      fast[d] = vld[d] != 0u && !far;
-      slow[d] = vld[d] != 0u && far;
-      rr[d] = y0[d] - (i0 + ady - CL_R);  // 0 .. CL_TH + 2 CL_R - 1 for fast items
-      if (tid == 0) tab[d].ybase = i0 + ady - CL_R;
-      if (fast[d]) {
-        atomicMin(&tab[d].xlo[rr[d]], x0[d]);
-        atomicMax(&tab[d].xhi[rr[d]], x0[d] + 1);
+      for (int d = 0; d < NDIRS; ++d) {
+        if (inimg) blm = __uint_as_float(max(__float_as_uint(blm), __float_as_uint(P.dir[d].blend ? fabsf(k.bl[d]) : 1.0f)));
+        // anchor vote: the displacement (x0 - j, y0 - i) of the tile's least displaced item, as one 32-bit key
+        const int dx = min(max(k.x0[d] - j, -1024), 1023), dy = min(max(k.y0[d] - i, -1024), 1023);
+        const unsigned mag = (unsigned)min(abs(dx) + abs(dy), 1023);
+        const unsigned key = k.vld[d] ? ((mag << 22) | (((unsigned)dx & 0x7ffu) << 11) | ((unsigned)dy & 0x7ffu)) : 0xffffffffu;
+        const unsigned best = __reduce_min_sync(0xffffffffu, key);
+        if (lane == 0 && best != 0xffffffffu) atomicMin(&tab[d].akey, best);
       }
-    }
-    cl_bar(1);
-    if (warp == 0) {
-      const int cmax = min(acc_words / (Cn + 1) - CL_ZPAD - 1, CL_SLOTS * (CL_NPIX / 2));
+      {
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(blm));  // NaN wins (bit patterns of non-negative floats)
+        if (lane == 0 && mb != 0u) atomicMax(&blmax_s, mb);
+      }
+      cl_bar(1);
+      bool fast[NDIRS], slow[NDIRS];
+      int rr[NDIRS];
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d) cl_tab_scan(tab[d], cmax);
-    }
-    cl_bar(1);
+      for (int d = 0; d < NDIRS; ++d) {
+        const unsigned ak = tab[d].akey;  // ~0 when no item of the tile has a tap
+        const int adx = ((int)(ak << 10)) >> 21, ady = ((int)(ak << 21)) >> 21;
+        const bool far = abs(k.x0[d] - j - adx) > CL_R || abs(k.y0[d] - i - ady) > CL_R;
+        fast[d] = k.vld[d] != 0u && !far;
+        slow[d] = k.vld[d] != 0u && far;
+        rr[d] = k.y0[d] - (i0 + ady - CL_R);  // 0 .. CL_TH + 2 CL_R - 1 for fast items
+        if (tid == 0) tab[d].ybase = i0 + ady - CL_R;
+        if (fast[d]) {
+          atomicMin(&tab[d].xlo[rr[d]], k.x0[d]);
+          atomicMax(&tab[d].xhi[rr[d]], k.x0[d] + 1);
+        }
+      }
+      cl_bar(1);
+      if (warp == 0) {
+        const int cmax = min(acc_words / (Cn + 1) - CL_ZPAD - 1, CL_SLOTS * (CL_NPIX / 2));
 #pragma unroll
-    for (int d = 0; d < NDIRS; ++d) {
-      const ClTab& T = tab[d];
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint2 o = make_uint2(0u, 0u);
-      if (fast[d] && T.ok) {
-        const float b = P.dir[d].blend ? bl[d] : 1.0f;
-        const float wl = b * ux[d], wr = b * tx[d];
-        w = make_float4(wl * uy[d], wr * uy[d], wl * ty[d], wr * ty[d]);
+        for (int d = 0; d < NDIRS; ++d) cl_tab_scan(tab[d], cmax);
+      }
+      cl_bar(1);
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        const ClTab& T = tab[d];
+        const float b = P.dir[d].blend ? k.bl[d] : 1.0f;
+        const float wl = b * k.ux[d], wr = b * k.tx[d];
+        float4 w = make_float4(wl * k.uy[d], wr * k.uy[d], wl * k.ty[d], wr * k.ty[d]);
         // taps outside the image (zeros padding) add nothing: their footprint cells only ever receive zeros
-        if (!(vld[d] & 1u)) w.x = 0.f;
-        if (!(vld[d] & 2u)) w.y = 0.f;
-        if (!(vld[d] & 4u)) w.z = 0.f;
-        if (!(vld[d] & 8u)) w.w = 0.f;
-        o.x = 4u * (unsigned)(T.rowbase[rr[d]] + (x0[d] - T.rowx[rr[d]]));
-        o.y = 4u * (unsigned)(T.rowbase[rr[d] + 1] + (x0[d] - T.rowx[rr[d] + 1]));
-      } else if (slow[d] || fast[d]) {
-        slow_s[atomicAdd(&nslow_s, 1)] = (unsigned short)((pp << 1) | d);
+        if (!(k.vld[d] & 1u)) w.x = 0.f;
+        if (!(k.vld[d] & 2u)) w.y = 0.f;
+        if (!(k.vld[d] & 4u)) w.z = 0.f;
+        if (!(k.vld[d] & 8u)) w.w = 0.f;
+        uint2 o = make_uint2(0u, 0u);
+        if (fast[d] && T.ok) {
+          o.x = 4u * (unsigned)(T.rowbase[rr[d]] + (k.x0[d] - T.rowx[rr[d]]));
+          o.y = 4u * (unsigned)(T.rowbase[rr[d] + 1] + (k.x0[d] - T.rowx[rr[d] + 1]));
+        } else {
+          if (slow[d] || fast[d]) {
+            const int slot = atomicAdd(&nslow_s, 1);
+            if (slot < CL_SLOWCAP) {
+              ClSlow e;
+              e.w[0] = w.x, e.w[1] = w.y, e.w[2] = w.z, e.w[3] = w.w;
+              e.goff = k.y0[d] * gsh[d] + k.x0[d];
+              e.key = (pp << 8) | (d << 4) | (int)k.vld[d];
+              slowtap[slot] = e;
+            } else {
+              slow_s[slot - CL_SLOWCAP] = (unsigned short)((pp << 1) | d);
+            }
+          }
+          w = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        wq[d * CL_NPIX + pp] = w;
+        oo[d * CL_NPIX + pp] = o;
       }
-      wq[d * CL_NPIX + pp] = w;
-      oo[d * CL_NPIX + pp] = o;
     }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ phase B, pixel role: kernel 2 on the texture units
+    __syncthreads();  // descriptors and tables -> channel role; the staged grad_out tile -> kernel 2
+    // ---- kernel 2 on the texture units
     // gix = sum_c gw_c [uy (b_c - a_c) + ty (d_c - c_c)] etc. (ATen grid_sampler_2d_backward): the weights do not depend on the
     // channel, so only the four sums  A_k = sum_c grad_out_c * tap_k,c  are accumulated per (pixel, direction) - one TLD4 and
     // four FFMA per channel - and the weights are applied once at the end.  The fetches run one batch ahead of the sums.
+    float fx1[NDIRS], fy1[NDIRS];
+    bool part = false;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      fx1[d] = k.vld[d] ? (float)(k.x0[d] + 1) : 0.0f;
+      fy1[d] = k.vld[d] ? (float)(k.y0[d] + 1) : 0.0f;
+      part |= k.vld[d] != 15u;
+    }
+    const bool masked = __any_sync(0xffffffffu, part);  // some tap of this warp is outside the image (borders, ragged tiles)
     float A[NDIRS][4];
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) A[d][0] = A[d][1] = A[d][2] = A[d][3] = 0.0f;
-    bool part = false;
-#pragma unroll
-    for (int d = 0; d < NDIRS; ++d) part |= vld[d] != 15u;
-    const bool masked = __any_sync(0xffffffffu, part);  // some tap of this warp is outside the image (borders, ragged tiles)
     const float fH = (float)G.H;
     const float* gq = gos + pp;
     for (int g = 0; g < G.n_groups; ++g) {
@@ -331,11 +397,11 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         th[d] = S.tex[blk];
         row0[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
       }
-      const float lastc = (float)(C - 1);
       auto fetchb = [&](int b, float4 (*q)[NDIRS]) {
 #pragma unroll
         for (int u = 0; u < CL_CB; ++u) {
-          const float cr = fminf((float)(b * CL_CB + u), lastc) * fH;  // past the end: the last plane again (its grad_out counts as 0)
+          const int c = min(b * CL_CB + u, C - 1);  // past the end: the last plane again (its grad_out counts as 0)
+          const float cr = (float)c * fH;
 #pragma unroll
           for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row0[d] + cr, 0);
         }
@@ -343,13 +409,12 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       auto consume = [&](int b, const float4 (*q)[NDIRS]) {
 #pragma unroll
         for (int u = 0; u < CL_CB; ++u) {
-          const int c = b * CL_CB + u;
-          const float gv = c < C ? gq[c * CL_GS] : 0.0f;
+          const float gv = (b * CL_CB + u < C) ? gq[(b * CL_CB + u) * CL_GS] : 0.0f;
 #pragma unroll
           for (int d = 0; d < NDIRS; ++d) {
             // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
             if (masked) {
-              const unsigned v = vld[d];
+              const unsigned v = k.vld[d];
               A[d][0] = fmaf(gv, (v & 1u) ? q[u][d].w : 0.0f, A[d][0]);
               A[d][1] = fmaf(gv, (v & 2u) ? q[u][d].z : 0.0f, A[d][1]);
               A[d][2] = fmaf(gv, (v & 4u) ? q[u][d].x : 0.0f, A[d][2]);
@@ -385,61 +450,72 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         const float a = A[d][0], b = A[d][1], cc = A[d][2], dd = A[d][3];
         float gbl = 0.0f, sc = 1.0f;
         if (P.dir[d].blend != nullptr) {
-          const float top = fmaf(b, tx[d], a * ux[d]), bot = fmaf(dd, tx[d], cc * ux[d]);
-          gbl = fmaf(bot, ty[d], top * uy[d]);
-          sc = bl[d];
+          const float top = fmaf(b, k.tx[d], a * k.ux[d]), bot = fmaf(dd, k.tx[d], cc * k.ux[d]);
+          gbl = fmaf(bot, k.ty[d], top * k.uy[d]);
+          sc = k.bl[d];
         }
-        const float gix = sc * fmaf(ty[d], dd - cc, uy[d] * (b - a));
-        const float giy = sc * fmaf(tx[d], dd - b, ux[d] * (cc - a));
-        const unsigned cb = clip >> (2 * d);
-        Tap k;
-        k.mx = (cb & 1u) ? 0.f : mxc;
-        k.my = (cb & 2u) ? 0.f : myc;
-        k.fx = k.fy = 0.f;
-        k.gate = 1.f;
+        const float gix = sc * fmaf(k.ty[d], dd - cc, k.uy[d] * (b - a));
+        const float giy = sc * fmaf(k.tx[d], dd - b, k.ux[d] * (cc - a));
+        const unsigned cb = k.clip >> (2 * d);
+        Tap kk;
+        kk.mx = (cb & 1u) ? 0.f : mxc;
+        kk.my = (cb & 2u) ? 0.f : myc;
+        kk.fx = kk.fy = 0.f;
+        kk.gate = 1.f;
         const DirP& D = P.dir[d];
         if (D.gate != nullptr) {
           const DirAt at = dir_at(D, n, t);
           const int of = i * (int)D.flow_sh + j;
-          k.fx = __ldg(at.flow + of);
-          k.fy = __ldg(at.flow + D.flow_sc + of);
-          k.gate = __ldg(at.gate + (i * (int)D.gate_sh + j));
+          kk.fx = __ldg(at.flow + of);
+          kk.fy = __ldg(at.flow + D.flow_sc + of);
+          kk.gate = __ldg(at.gate + (i * (int)D.gate_sh + j));
         }
-        bwdflow_store(P, Q, d, n, t, i, j, k, gix, giy, gbl);
+        bwdflow_store(P, Q, d, n, t, i, j, kk, gix, giy, gbl);
       }
     }
     return;
   }
 
-  // -------------------------------------------------------------------- phase A, channel role: grad_out tile -> shared memory
-  if (warp == 8) {  // channel tables over the groups that have a grad_out (the others contribute nothing)
+  // ====================================================================== channel role: kernel 3 (scatter into grad_src)
+  if (CL_DBG & 2) return;
+#if CL_REGS_K3
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CL_REGS_K3));
+#endif
+  const int ctid = tid - CL_NPIX;
+  // ---- the grad_out tile travels to shared memory (4-byte cp.async: any plane stride) while the taps are computed.
+  // Out-of-image pixels of ragged tiles stage the value of the clamped address: their items carry zero weights.
+  {
+    unsigned gd = (unsigned)__cvta_generic_to_shared(gos + pp);
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const float* gp = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
+      const int C = P.grp[g].C;
+      const long long sc = Q.go_sc[g];
+#pragma unroll 4
+      for (int c = 0; c < C; ++c) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gd), "l"(gp) : "memory");
+        gp += sc;
+        gd += 4u * CL_GS;
+      }
+    }
+    cp_async_commit();
+  }
+  if (warp == 8) {  // channel table over the groups that have a grad_out (the others contribute nothing)
     int base = 0;
     unsigned m0 = 0u, m1 = 0u;
     for (int g = 0; g < G.n_groups; ++g) {
       if (!Q.grad_out[g]) continue;
       const int C = P.grp[g].C;
       ClChan e;
-      ClTex x;
       e.g = g;
       e.c = lane;
-      e.pad_[0] = e.pad_[1] = x.pad_[0] = x.pad_[1] = 0;
+      e.pad_[0] = e.pad_[1] = 0;
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
         float* gs = (d < NDIRS && lane < C) ? Q.grad_src[g][d] : nullptr;
         e.gs[d] = gs ? gs + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)lane * Q.gs_sc[g][d] : nullptr;
-        x.tex[d] = 0ull;
-        x.row[d] = 0.0f;
-        if (d < NDIRS) {
-          const TexSrc& S = X.s[g][d];
-          const int blk = n / S.nb;
-          x.tex[d] = S.tex[blk];
-          x.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t + lane * G.H);
-        }
       }
-      if (lane < C) {
-        chan[base + lane] = e;
-        ctex[base + lane] = x;
-      }
+      if (lane < C) chan[base + lane] = e;
       m0 |= __ballot_sync(0xffffffffu, e.gs[0] != nullptr) << base;
       m1 |= __ballot_sync(0xffffffffu, e.gs[1] != nullptr) << base;
       base += C;
@@ -451,37 +527,17 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       gsmask_s[1] = m1;
     }
   }
-  {
-    // out-of-image pixels of ragged tiles stage the value of the clamped address: their items carry zero weights
-    float* gd = gos + pp;
-    for (int g = 0; g < G.n_groups; ++g) {
-      if (!Q.grad_out[g]) continue;
-      const float* gp = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
-      const int C = P.grp[g].C;
-      const long long sc = Q.go_sc[g];
-      int c = 0;
-      for (; c + 4 <= C; c += 4) {
-        float v[4];
+  int gsh[NDIRS];  // row stride of the grad_src planes per direction (all groups agree, host-checked)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = __ldcs(gp);
-          gp += sc;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gd[u * CL_GS] = v[u];
-        gd += 4 * CL_GS;
-      }
-      for (; c < C; ++c) {
-        *gd = __ldcs(gp);
-        gp += sc;
-        gd += CL_GS;
-      }
-    }
+  for (int d = 0; d < NDIRS; ++d) {
+    gsh[d] = 0;
+    for (int g = G.n_groups - 1; g >= 0; --g)
+      if (Q.grad_out[g] && Q.grad_src[g][d]) gsh[d] = Q.gs_sh[g][d];
   }
+  cp_async_wait<0>();
   __syncthreads();
 
-  // -------------------------------------------------------------------- phase B, channel role: scatter + flush
-  const int ctid = tid - CL_NPIX;
+
   int* const acc = reinterpret_cast<int*>(gos + ((Cn * CL_GS + 3) & ~3));
   const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
   constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: fma(x, y, MAGIC) holds round-to-nearest(x*y) in its low mantissa bits
@@ -541,10 +597,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       }
     }
     cl_bar(2);
-    int gsh = 0;
-    for (int g = G.n_groups - 1; g >= 0; --g)
-      if (Q.grad_out[g] && Q.grad_src[g][d]) gsh = Q.gs_sh[g][d];  // all groups agree (host-checked)
-    // two halves of 128 threads, half h takes the planes cf = h, h + 2, ...
+    // flush: two halves of 128 threads, half h takes the planes cf = h, h + 2, ...
     const int half = ctid >> 7, htid = ctid & 127;
     const int nsl = (T.cells + CL_NPIX / 2 - 1) / (CL_NPIX / 2);
     int goff[CL_SLOTS], cmb[CL_SLOTS];
@@ -563,7 +616,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
           const int y = T.ybase + r, col = T.rowx[r] + (kk - T.rowoff[r]);
           const int cnt = acc[Cn * PS + CL_ZPAD + kk];
           // a cell outside the image only ever received zeros (weights masked): it adds 0.0 at the clamped address
-          goff[s] = min(max(y, 0), G.H - 1) * gsh + min(max(col, 0), G.W - 1);
+          goff[s] = min(max(y, 0), G.H - 1) * gsh[d] + min(max(col, 0), G.W - 1);
           cmb[s] = -cnt * MAGIC_BITS;
           if (s == nsl - 1) last_on = true;
         }
@@ -597,8 +650,16 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   }
   // SLOW items, and every item of a non-finite channel: exact float atomics, lane = channel
   const int nslow = nslow_s;
-  for (int q = pw; q < nslow; q += 8) {
-    const int e = slow_s[q], sp = e >> 1, sd = e & 1;
+  for (int q = pw; q < min(nslow, CL_SLOWCAP); q += 8) {
+    const ClSlow& e = slowtap[q];
+    const int sp = e.key >> 8, sd = (e.key >> 4) & 1;
+    if (lane < Cn) {
+      float* gs = chan[lane].gs[sd];
+      if (gs) cl_scatter_exact(gs + e.goff, gsh[sd], (unsigned)e.key & 15u, e.w, gos[lane * CL_GS + sp]);
+    }
+  }
+  for (int q = CL_SLOWCAP + pw; q < nslow; q += 8) {
+    const int e = slow_s[q - CL_SLOWCAP], sp = e >> 1, sd = e & 1;
     const int sw = sp >> 5, sl = sp & 31;
     const int sj = blockIdx.x * CL_TW + (sw & 3) * 8 + (sl & 7), si = blockIdx.y * CL_TH + (sw >> 2) * 4 + (sl >> 3);
     cl_exact_item<NDIRS>(P, Q, chan, gos, Cn, n, t, si, sj, sp, sd, true);
