@@ -329,7 +329,7 @@ static void env_load_locked() {
   e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
   e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 46);
   e.bwdx_ppt = env_int("FWB_BWDX_PPT", 2);
-  e.cl_kb = env_int("FWB_CL_KB", 93);
+  e.cl_kb = env_int("FWB_CL_KB", 96);
   e.cl_minc = env_int("FWB_CL_MINC", 12);
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);
@@ -1017,6 +1017,9 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
           bool cl_fits = acc_words >= (Cgo + 1) * (CL_ZPAD + 64);
           for (int gi = 0; gi < p->n_groups; ++gi)
             if (Q.grad_out[gi] && (long long)Q.go_sc[gi] * p->grp[gi].C >= 2147483647LL) cl_fits = false;
+          for (int gi = 0; gi < p->n_groups; ++gi)
+            for (int d = 0; d < p->n_dirs; ++d)
+              if (Q.grad_src[gi][d] && ((long long)Q.gs_sc[gi][d] * (p->grp[gi].C + 1) + (long long)(p->H + 1) * Q.gs_sh[gi][d]) >= 2147483647LL) cl_fits = false;
           if (cl_fits) {
             const dim3 gc((p->W + CL_TW - 1) / CL_TW, (p->H + CL_TH - 1) / CL_TH, p->N * p->T);
 #define FWB_LAUNCH_CL(D, A, B)                                                \

@@ -37,7 +37,7 @@ constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the st
 #define CL_CB_N 1
 #endif
 #ifndef CL_DBG
-#define CL_DBG 0  // 1: the pixel role returns at once, 2: the channel role returns at once (timing experiments)
+#define CL_DBG 0  // 2: the channel role returns after staging grad_out (timing experiment: the pixel role alone)
 #endif
 #ifndef CL_REGS_K2
 #define CL_REGS_K2 0  // setmaxnreg of the pixel-role warps (0: leave the launch value)
@@ -49,6 +49,12 @@ struct ClChan {  // per flattened channel (groups that have a grad_out)
   float* gs[2];  // grad_src plane of (n, t, c) per direction, or NULL
   int g, c;
   int pad_[2];
+};
+
+struct ClGrp {  // per group that has a grad_out: where the flush finds its grad_src planes
+  float* gsb[2];  // grad_src of (n, t, channel 0) per direction, or NULL
+  int gsc[2];     // plane stride
+  int C, cf0;     // channels, first flattened channel
 };
 
 struct ClTab {  // footprint of one direction: row r is source row ybase + r, columns [rowx, rowx + len) at word rowbase of a plane
@@ -121,14 +127,15 @@ __device__ __forceinline__ void cl_exact_item(const Params& P, const GradP& Q, c
 // scatter), * Sinv = float.  Cells outside the image / without a tap add an exact 0 at a clamped address; only the last slot
 // (ragged: cells past the end of the footprint) is predicated.
 template <int NSL>
-__device__ __forceinline__ void cl_flush_planes(float* gsp, long long gstep, int np, const float* sinv, unsigned ap, unsigned ap_step,
+__device__ __forceinline__ void cl_flush_planes(float* gsp, int gstep, int np, const float* sinv, unsigned ap, unsigned ap_step,
                                                 const int* goff, const int* cmb, bool last_on) {
   // (opaque copies: keep the strides in registers instead of re-deriving them from the kernel parameters in the loop)
-  asm volatile("" : "+l"(gstep));
+  asm volatile("" : "+r"(gstep));
   asm volatile("" : "+r"(ap_step));
-  float* p[NSL];
+  asm volatile("" : "+l"(gsp));
+  int off[NSL];  // element offset of the cell in the current plane, relative to gsp (host-checked: fits in 32 bits)
 #pragma unroll
-  for (int s = 0; s < NSL; ++s) p[s] = gsp + goff[s];
+  for (int s = 0; s < NSL; ++s) off[s] = goff[s];
 #pragma unroll 1
   for (int q = 0; q < np; ++q) {
     const float Sinv = sinv[2 * q];
@@ -137,9 +144,9 @@ __device__ __forceinline__ void cl_flush_planes(float* gsp, long long gstep, int
       if (s < NSL - 1 || last_on) {
         int raw;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(raw) : "r"(ap + (unsigned)(s * (CL_NPIX / 2) * 4)));
-        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p[s]), "f"((float)(raw + cmb[s]) * Sinv) : "memory");
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gsp + off[s]), "f"((float)(raw + cmb[s]) * Sinv) : "memory");
       }
-      p[s] += gstep;
+      off[s] += gstep;
     }
     ap += ap_step;
   }
@@ -201,12 +208,6 @@ __device__ __forceinline__ void cl_taps(const Params& P, int n, int t, int ic, i
   }
 }
 
-struct ClSlow {  // a SLOW item with its taps: float atomics straight to global memory
-  float w[4];   // bilinear weights * blend
-  int goff;     // y0 * row stride + x0 inside a grad_src plane
-  int key;      // pixel << 8 | direction << 4 | validity bits
-};
-constexpr int CL_SLOWCAP = 96;
 
 // grad_src[tap] += w_tap * g for the 4 taps of one item in one plane (ATen grid_sampler_2d_backward's atomicAdd scatter); the
 // (x0, x0+1) pair of a row goes out as one 8-byte vector reduction when both taps are inside the image and the pair is aligned
@@ -232,15 +233,14 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   extern __shared__ float4 cl_smem4[];
   __shared__ ClTab tab[NDIRS];
   __shared__ __align__(16) ClChan chan[CL_MAXC];
+  __shared__ __align__(16) ClGrp grp_s[FWB_MAX_GROUPS];
+  __shared__ int ngrp_s;
   __shared__ __align__(16) float4 wq[NDIRS * CL_NPIX];  // item (p, d) at d * 256 + p: bilinear weights * blend
   __shared__ __align__(8) uint2 oo[NDIRS * CL_NPIX];    //                           byte offsets of the nw / sw taps inside a plane
-  __shared__ __align__(8) ClSlow slowtap[CL_SLOWCAP];
   __shared__ unsigned amax_s[32];
   __shared__ float sinv_s[32];
   __shared__ float zeros_s[32];
-  __shared__ unsigned short slow_s[NDIRS * CL_NPIX];  // (p << 1) | d: SLOW items beyond the capacity of slowtap
   __shared__ unsigned blmax_s;
-  __shared__ int nslow_s;
   __shared__ unsigned gsmask_s[2];  // per direction: channels (bits) that have a grad_src plane
 
   const Geo& G = P.geo;
@@ -266,12 +266,12 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
 
   if (warp < 8) {
     // ==================================================================== pixel role
-    if (CL_DBG & 1) return;
 #if CL_REGS_K2
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CL_REGS_K2));
 #endif
     ClTaps<NDIRS> k;
     cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic, jc, inimg, k);
+    unsigned slowbits = 0u;
     {
       // ---- footprint tables and item descriptors of the scatter (thread = pixel; barrier 1 = the 8 pixel warps)
       for (int q = tid; q < NDIRS * CL_ROWS; q += CL_NPIX) {
@@ -281,17 +281,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         T.xhi[r] = -0x7fffffff;
       }
       if (tid < NDIRS) tab[tid].akey = 0xffffffffu;
-      if (tid == 0) {
-        nslow_s = 0;
-        blmax_s = 0u;
-      }
-      int gsh[NDIRS];  // row stride of the grad_src planes per direction (all groups agree, host-checked)
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        gsh[d] = 0;
-        for (int g = G.n_groups - 1; g >= 0; --g)
-          if (Q.grad_out[g] && Q.grad_src[g][d]) gsh[d] = Q.gs_sh[g][d];
-      }
+      if (tid == 0) blmax_s = 0u;
       cl_bar(1);
       float blm = 0.f;
 #pragma unroll
@@ -348,18 +338,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
           o.x = 4u * (unsigned)(T.rowbase[rr[d]] + (k.x0[d] - T.rowx[rr[d]]));
           o.y = 4u * (unsigned)(T.rowbase[rr[d] + 1] + (k.x0[d] - T.rowx[rr[d] + 1]));
         } else {
-          if (slow[d] || fast[d]) {
-            const int slot = atomicAdd(&nslow_s, 1);
-            if (slot < CL_SLOWCAP) {
-              ClSlow e;
-              e.w[0] = w.x, e.w[1] = w.y, e.w[2] = w.z, e.w[3] = w.w;
-              e.goff = k.y0[d] * gsh[d] + k.x0[d];
-              e.key = (pp << 8) | (d << 4) | (int)k.vld[d];
-              slowtap[slot] = e;
-            } else {
-              slow_s[slot - CL_SLOWCAP] = (unsigned short)((pp << 1) | d);
-            }
-          }
+          if (slow[d] || fast[d]) slowbits |= 1u << d;  // SLOW: this thread scatters the item itself after kernel 2
           w = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         wq[d * CL_NPIX + pp] = w;
@@ -397,46 +376,54 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         th[d] = S.tex[blk];
         row0[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
       }
-      auto fetchb = [&](int b, float4 (*q)[NDIRS]) {
-#pragma unroll
-        for (int u = 0; u < CL_CB; ++u) {
-          const int c = min(b * CL_CB + u, C - 1);  // past the end: the last plane again (its grad_out counts as 0)
-          const float cr = (float)c * fH;
-#pragma unroll
-          for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row0[d] + cr, 0);
+      auto acc4 = [&](const float4& q, float gv, int d) {
+        // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
+        if (masked) {
+          const unsigned v = k.vld[d];
+          A[d][0] = fmaf(gv, (v & 1u) ? q.w : 0.0f, A[d][0]);
+          A[d][1] = fmaf(gv, (v & 2u) ? q.z : 0.0f, A[d][1]);
+          A[d][2] = fmaf(gv, (v & 4u) ? q.x : 0.0f, A[d][2]);
+          A[d][3] = fmaf(gv, (v & 8u) ? q.y : 0.0f, A[d][3]);
+        } else {
+          A[d][0] = fmaf(gv, q.w, A[d][0]);
+          A[d][1] = fmaf(gv, q.z, A[d][1]);
+          A[d][2] = fmaf(gv, q.x, A[d][2]);
+          A[d][3] = fmaf(gv, q.y, A[d][3]);
         }
       };
-      auto consume = [&](int b, const float4 (*q)[NDIRS]) {
+      // the quads of channel c + 1 travel while those of channel c are summed
+      float4 qa[NDIRS], qb[NDIRS];
+      float row[NDIRS];
 #pragma unroll
-        for (int u = 0; u < CL_CB; ++u) {
-          const float gv = (b * CL_CB + u < C) ? gq[(b * CL_CB + u) * CL_GS] : 0.0f;
+      for (int d = 0; d < NDIRS; ++d) {
+        row[d] = row0[d];
+        qa[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < C; c += 2) {
+        const bool more1 = c + 1 < C, more2 = c + 2 < C;
+        if (more1) {
 #pragma unroll
           for (int d = 0; d < NDIRS; ++d) {
-            // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
-            if (masked) {
-              const unsigned v = k.vld[d];
-              A[d][0] = fmaf(gv, (v & 1u) ? q[u][d].w : 0.0f, A[d][0]);
-              A[d][1] = fmaf(gv, (v & 2u) ? q[u][d].z : 0.0f, A[d][1]);
-              A[d][2] = fmaf(gv, (v & 4u) ? q[u][d].x : 0.0f, A[d][2]);
-              A[d][3] = fmaf(gv, (v & 8u) ? q[u][d].y : 0.0f, A[d][3]);
-            } else {
-              A[d][0] = fmaf(gv, q[u][d].w, A[d][0]);
-              A[d][1] = fmaf(gv, q[u][d].z, A[d][1]);
-              A[d][2] = fmaf(gv, q[u][d].x, A[d][2]);
-              A[d][3] = fmaf(gv, q[u][d].y, A[d][3]);
-            }
+            row[d] += fH;  // integers below 2^24: exact
+            qb[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
           }
         }
-      };
-      const int nb = (C + CL_CB - 1) / CL_CB;
-      float4 qa[CL_CB][NDIRS], qb[CL_CB][NDIRS];
-      fetchb(0, qa);
-#pragma unroll 1
-      for (int b = 0; b < nb; b += 2) {
-        if (b + 1 < nb) fetchb(b + 1, qb);
-        consume(b, qa);
-        if (b + 2 < nb) fetchb(b + 2, qa);
-        if (b + 1 < nb) consume(b + 1, qb);
+        const float g0v = gq[c * CL_GS];
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) acc4(qa[d], g0v, d);
+        if (more2) {
+#pragma unroll
+          for (int d = 0; d < NDIRS; ++d) {
+            row[d] += fH;
+            qa[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
+          }
+        }
+        if (more1) {
+          const float g1v = gq[(c + 1) * CL_GS];
+#pragma unroll
+          for (int d = 0; d < NDIRS; ++d) acc4(qb[d], g1v, d);
+        }
       }
       gq += C * CL_GS;
     }
@@ -473,11 +460,34 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         bwdflow_store(P, Q, d, n, t, i, j, kk, gix, giy, gbl);
       }
     }
+    // ---- SLOW items (taps far from the rest of the tile, or a direction whose footprint does not fit): this thread owns the
+    // taps, so it adds its contributions straight to global memory (exact float reductions; grad_out from the staged tile)
+    if (slowbits) {
+#pragma unroll
+      for (int d = 0; d < NDIRS; ++d) {
+        if (!((slowbits >> d) & 1u)) continue;
+        const float b = P.dir[d].blend ? k.bl[d] : 1.0f;
+        const float wl = b * k.ux[d], wr = b * k.tx[d];
+        const float w[4] = {wl * k.uy[d], wr * k.uy[d], wl * k.ty[d], wr * k.ty[d]};
+        const float* gv = gos + pp;
+        for (int g = 0; g < G.n_groups; ++g) {
+          if (!Q.grad_out[g]) continue;
+          const int C = P.grp[g].C;
+          float* gs = Q.grad_src[g][d];
+          if (gs) {
+            const int sh = Q.gs_sh[g][d];
+            gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)k.y0[d] * sh + k.x0[d];
+            const long long gsc = Q.gs_sc[g][d];
+            for (int c = 0; c < C; ++c) cl_scatter_exact(gs + c * gsc, sh, k.vld[d], w, gv[c * CL_GS]);
+          }
+          gv += C * CL_GS;
+        }
+      }
+    }
     return;
   }
 
   // ====================================================================== channel role: kernel 3 (scatter into grad_src)
-  if (CL_DBG & 2) return;
 #if CL_REGS_K3
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CL_REGS_K3));
 #endif
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     cp_async_commit();
   }
   if (warp == 8) {  // channel table over the groups that have a grad_out (the others contribute nothing)
-    int base = 0;
+    int base = 0, ng = 0;
     unsigned m0 = 0u, m1 = 0u;
     for (int g = 0; g < G.n_groups; ++g) {
       if (!Q.grad_out[g]) continue;
@@ -516,6 +526,18 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         e.gs[d] = gs ? gs + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)lane * Q.gs_sc[g][d] : nullptr;
       }
       if (lane < C) chan[base + lane] = e;
+      if (lane == 0) {
+        ClGrp gr;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          gr.gsb[d] = e.gs[d];  // lane 0: channel 0 of the group
+          gr.gsc[d] = d < NDIRS ? Q.gs_sc[g][d] : 0;
+        }
+        gr.C = C;
+        gr.cf0 = base;
+        grp_s[ng] = gr;
+      }
+      ++ng;
       m0 |= __ballot_sync(0xffffffffu, e.gs[0] != nullptr) << base;
       m1 |= __ballot_sync(0xffffffffu, e.gs[1] != nullptr) << base;
       base += C;
@@ -525,6 +547,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     if (lane == 0) {
       gsmask_s[0] = m0;
       gsmask_s[1] = m1;
+      ngrp_s = ng;
     }
   }
   int gsh[NDIRS];  // row stride of the grad_src planes per direction (all groups agree, host-checked)
@@ -536,6 +559,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   }
   cp_async_wait<0>();
   __syncthreads();
+  if (CL_DBG & 2) return;  // timing experiment: the pixel role alone
 
 
   int* const acc = reinterpret_cast<int*>(gos + ((Cn * CL_GS + 3) & ~3));
@@ -549,34 +573,38 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     for (int u = 0; u < 32; ++u) m = max(m, __float_as_uint(gl[u]) & 0x7fffffffu);
     if (m != 0u) atomicMax(&amax_s[lane], m);
   }
-  cl_bar(2);
-  // scale of this lane's channel
-  float S = 0.f;
-  bool finite = true;
-  if (lane < Cn) {
-    const unsigned ab = amax_s[lane], bb = blmax_s;
-    const float prod = __uint_as_float(ab) * __uint_as_float(bb);
-    const unsigned pb = __float_as_uint(prod);
-    finite = ab < 0x7f800000u && bb < 0x7f800000u && pb < 0x7f800000u;
-    const int sexp = min(252, max(2, 274 - (int)(pb >> 23)));  // biased exponent of 2^(20 - exponent(amax))
-    if (finite && pb != 0u) S = __uint_as_float((unsigned)sexp << 23);
-    if (warp == 8) sinv_s[lane] = (finite && pb != 0u) ? __uint_as_float((unsigned)(254 - sexp) << 23) : 0.f;
-  }
-  const bool any_nonfinite = __any_sync(0xffffffffu, !finite);
-  if (lane >= Cn || !finite) gl = zeros_s;  // the tap counter lane and non-finite channels put in exact zeros
-  // lane Cn counts the taps per cell: fma(0, w, denorm_min) has the bit pattern 1
-  const float magic = lane == Cn ? __int_as_float(1) : MAGIC;
+  float S = 0.f, magic = 0.f;
+  bool finite = true, any_nonfinite = false, scaled = false;
 #pragma unroll 1
-  for (int d = 0; d < NDIRS; ++d) {
-    const ClTab& T = tab[d];
-    const unsigned gsm = gsmask_s[d];
-    if (!T.ok || T.cells == 0 || gsm == 0u) continue;  // (uniform) nothing to scatter in this direction
+  for (int d = 0; d <= NDIRS; ++d) {
+    // (one more round than there are directions: the scale of the channels is needed even when no direction scatters)
+    const bool live = d < NDIRS && tab[d < NDIRS ? d : 0].ok && tab[d < NDIRS ? d : 0].cells != 0 && gsmask_s[d < NDIRS ? d : 0] != 0u;
+    if (!live && (scaled || d < NDIRS)) continue;  // (uniform)
+    const ClTab& T = tab[d < NDIRS ? d : 0];
+    const unsigned gsm = live ? gsmask_s[d] : 0u;
     const int PS = (CL_ZPAD + T.cells) | 1;
-    {  // clear the planes (and the tap counter plane)
+    if (live) {  // clear the planes (and the tap counter plane)
       const int n4 = ((Cn + 1) * PS + 3) >> 2;
       for (int q = ctid; q < n4; q += CL_NPIX) asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + 16u * (unsigned)q), "r"(0) : "memory");
     }
-    cl_bar(2);
+    cl_bar(2);  // the planes are clear; (first round) the maxima of all eight warps are in
+    if (!scaled) {  // scale of this lane's channel
+      scaled = true;
+      if (lane < Cn) {
+        const unsigned ab = amax_s[lane], bb = blmax_s;
+        const float prod = __uint_as_float(ab) * __uint_as_float(bb);
+        const unsigned pb = __float_as_uint(prod);
+        finite = ab < 0x7f800000u && bb < 0x7f800000u && pb < 0x7f800000u;
+        const int sexp = min(252, max(2, 274 - (int)(pb >> 23)));  // biased exponent of 2^(20 - exponent(amax))
+        if (finite && pb != 0u) S = __uint_as_float((unsigned)sexp << 23);
+        if (warp == 8) sinv_s[lane] = (finite && pb != 0u) ? __uint_as_float((unsigned)(254 - sexp) << 23) : 0.f;
+      }
+      any_nonfinite = __any_sync(0xffffffffu, !finite);
+      if (lane >= Cn || !finite) gl = zeros_s;  // the tap counter lane and non-finite channels put in exact zeros
+      // lane Cn counts the taps per cell: fma(0, w, denorm_min) has the bit pattern 1
+      magic = lane == Cn ? __int_as_float(1) : MAGIC;
+    }
+    if (!live) continue;
     if (lane <= Cn) {
       // every tap adds the raw bits of fma(g * S, w, MAGIC) = MAGIC_BITS + k (k = the rounded fixed-point product); a cell hit
       // by cnt taps then holds cnt * MAGIC_BITS + sum k (mod 2^32): the flush takes cnt * MAGIC_BITS off again
@@ -624,46 +652,29 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     }
     const unsigned ps_b = 4u * (unsigned)PS;
     const unsigned ap0 = acc_s + 4u * (unsigned)(CL_ZPAD + htid);
-    int cf = 0;
-    for (int g = 0; g < G.n_groups; ++g) {
-      if (!Q.grad_out[g]) continue;
-      const int C = P.grp[g].C;
-      if (Q.grad_src[g][d]) {
-        const int c0 = (half ^ cf) & 1;  // first channel of this group whose flattened index has this half's parity
-        const int np = (C - c0 + 1) >> 1;
-        const long long gsc = Q.gs_sc[g][d];
-        float* gsp = Q.grad_src[g][d] + n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + c0 * gsc;
-        const unsigned ap = ap0 + ps_b * (unsigned)(cf + c0);
-        const float* si = sinv_s + cf + c0;
-        switch (nsl) {
-          case 1: cl_flush_planes<1>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-          case 2: cl_flush_planes<2>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-          case 3: cl_flush_planes<3>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-          case 4: cl_flush_planes<4>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-          case 5: cl_flush_planes<5>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-          default: cl_flush_planes<6>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
-        }
+    const int ngrp = ngrp_s;
+    for (int gq_ = 0; gq_ < ngrp; ++gq_) {
+      const ClGrp& GR = grp_s[gq_];
+      float* gsb = GR.gsb[d];
+      if (!gsb) continue;
+      const int C = GR.C, cf = GR.cf0, gsc = GR.gsc[d];
+      const int c0 = (half ^ cf) & 1;  // first channel of this group whose flattened index has this half's parity
+      const int np = (C - c0 + 1) >> 1;
+      float* gsp = gsb + (long long)c0 * gsc;
+      const unsigned ap = ap0 + ps_b * (unsigned)(cf + c0);
+      const float* si = sinv_s + cf + c0;
+      switch (nsl) {
+        case 1: cl_flush_planes<1>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        case 2: cl_flush_planes<2>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        case 3: cl_flush_planes<3>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        case 4: cl_flush_planes<4>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        case 5: cl_flush_planes<5>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
+        default: cl_flush_planes<6>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
       }
-      cf += C;
     }
-    if (d + 1 < NDIRS) cl_bar(2);  // the planes are reused by the next direction
+    cl_bar(2);  // the planes are reused by the next direction; sinv_s is read by every warp
   }
-  // SLOW items, and every item of a non-finite channel: exact float atomics, lane = channel
-  const int nslow = nslow_s;
-  for (int q = pw; q < min(nslow, CL_SLOWCAP); q += 8) {
-    const ClSlow& e = slowtap[q];
-    const int sp = e.key >> 8, sd = (e.key >> 4) & 1;
-    if (lane < Cn) {
-      float* gs = chan[lane].gs[sd];
-      if (gs) cl_scatter_exact(gs + e.goff, gsh[sd], (unsigned)e.key & 15u, e.w, gos[lane * CL_GS + sp]);
-    }
-  }
-  for (int q = CL_SLOWCAP + pw; q < nslow; q += 8) {
-    const int e = slow_s[q - CL_SLOWCAP], sp = e >> 1, sd = e & 1;
-    const int sw = sp >> 5, sl = sp & 31;
-    const int sj = blockIdx.x * CL_TW + (sw & 3) * 8 + (sl & 7), si = blockIdx.y * CL_TH + (sw >> 2) * 4 + (sl >> 3);
-    cl_exact_item<NDIRS>(P, Q, chan, gos, Cn, n, t, si, sj, sp, sd, true);
-  }
+  // every (fast) item of a non-finite channel: exact float atomics, lane = channel
   if (any_nonfinite) {
     for (int u = 0; u < 32; ++u) {
       const int sp = (pw << 5) | u;
