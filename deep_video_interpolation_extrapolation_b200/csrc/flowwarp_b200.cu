@@ -329,7 +329,7 @@ static void env_load_locked() {
   e.tile_bwdf_kb = env_int("FWB_TILE_BWDF_KB", 52);
   e.tile_bwdx_kb = env_int("FWB_TILE_BWDX_KB", 46);
   e.bwdx_ppt = env_int("FWB_BWDX_PPT", 2);
-  e.cl_kb = env_int("FWB_CL_KB", 96);
+  e.cl_kb = env_int("FWB_CL_KB", 95);
   e.cl_minc = env_int("FWB_CL_MINC", 12);
   g_env = e;
   g_env_ready.store(1, std::memory_order_release);

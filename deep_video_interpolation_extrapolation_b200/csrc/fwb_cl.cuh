@@ -209,6 +209,13 @@ __device__ __forceinline__ void cl_taps(const Params& P, int n, int t, int ic, i
 }
 
 
+struct ClSlow {  // a SLOW item with its taps (the first CL_SLOWCAP of a tile; the rest are scattered by their owner threads)
+  float w[4];   // bilinear weights * blend
+  int goff;     // y0 * row stride + x0 inside a grad_src plane
+  int key;      // pixel << 8 | direction << 4 | validity bits
+};
+constexpr int CL_SLOWCAP = 64;
+
 // grad_src[tap] += w_tap * g for the 4 taps of one item in one plane (ATen grid_sampler_2d_backward's atomicAdd scatter); the
 // (x0, x0+1) pair of a row goes out as one 8-byte vector reduction when both taps are inside the image and the pair is aligned
 __device__ __forceinline__ void cl_scatter_exact(float* gs, int sh, unsigned vld, const float* w, float g) {
@@ -237,6 +244,8 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   __shared__ int ngrp_s;
   __shared__ __align__(16) float4 wq[NDIRS * CL_NPIX];  // item (p, d) at d * 256 + p: bilinear weights * blend
   __shared__ __align__(8) uint2 oo[NDIRS * CL_NPIX];    //                           byte offsets of the nw / sw taps inside a plane
+  __shared__ __align__(8) ClSlow slowtap[CL_SLOWCAP];
+  __shared__ int nslow_s, nfar_s;
   __shared__ unsigned amax_s[32];
   __shared__ float sinv_s[32];
   __shared__ float zeros_s[32];
@@ -281,7 +290,11 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         T.xhi[r] = -0x7fffffff;
       }
       if (tid < NDIRS) tab[tid].akey = 0xffffffffu;
-      if (tid == 0) blmax_s = 0u;
+      if (tid == 0) {
+        blmax_s = 0u;
+        nslow_s = 0;
+        nfar_s = 0;
+      }
       cl_bar(1);
       float blm = 0.f;
 #pragma unroll
@@ -314,6 +327,8 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
           atomicMin(&tab[d].xlo[rr[d]], k.x0[d]);
           atomicMax(&tab[d].xhi[rr[d]], k.x0[d] + 1);
         }
+        const unsigned fm = __ballot_sync(0xffffffffu, slow[d]);
+        if (lane == 0 && fm) atomicAdd(&nfar_s, __popc(fm));
       }
       cl_bar(1);
       if (warp == 0) {
@@ -338,7 +353,23 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
           o.x = 4u * (unsigned)(T.rowbase[rr[d]] + (k.x0[d] - T.rowx[rr[d]]));
           o.y = 4u * (unsigned)(T.rowbase[rr[d] + 1] + (k.x0[d] - T.rowx[rr[d] + 1]));
         } else {
-          if (slow[d] || fast[d]) slowbits |= 1u << d;  // SLOW: this thread scatters the item itself after kernel 2
+          if (slow[d] || fast[d]) {
+            // SLOW: a few outliers per tile go to the channel role with their taps (lanes = channels); when there are many
+            // (large displacements, a footprint that does not fit) every thread scatters its own items after kernel 2
+            const int slot = (slow[d] && nfar_s <= CL_SLOWCAP) ? atomicAdd(&nslow_s, 1) : CL_SLOWCAP;
+            if (slot < CL_SLOWCAP) {
+              int sh = 0;
+              for (int g = G.n_groups - 1; g >= 0; --g)
+                if (Q.grad_out[g] && Q.grad_src[g][d]) sh = Q.gs_sh[g][d];
+              ClSlow e;
+              e.w[0] = w.x, e.w[1] = w.y, e.w[2] = w.z, e.w[3] = w.w;
+              e.goff = k.y0[d] * sh + k.x0[d];
+              e.key = (pp << 8) | (d << 4) | (int)k.vld[d];
+              slowtap[slot] = e;
+            } else {
+              slowbits |= 1u << d;
+            }
+          }
           w = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         wq[d * CL_NPIX + pp] = w;
@@ -673,6 +704,18 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       }
     }
     cl_bar(2);  // the planes are reused by the next direction; sinv_s is read by every warp
+  }
+  // the cached SLOW items: exact float reductions, lane = channel
+  {
+    const int nslow = min(nslow_s, CL_SLOWCAP);
+    for (int q = pw; q < nslow; q += 8) {
+      const ClSlow& e = slowtap[q];
+      const int sp = e.key >> 8, sd = (e.key >> 4) & 1;
+      if (lane < Cn) {
+        float* gs = chan[lane].gs[sd];
+        if (gs) cl_scatter_exact(gs + e.goff, gsh[sd], (unsigned)e.key & 15u, e.w, gos[lane * CL_GS + sp]);
+      }
+    }
   }
   // every (fast) item of a non-finite channel: exact float atomics, lane = channel
   if (any_nonfinite) {
