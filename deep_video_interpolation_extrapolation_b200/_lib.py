@@ -96,6 +96,10 @@ class fwb_label_problem(C.Structure):
     ]
 
 
+class fwb_view(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sn", i64), ("st", i64), ("sc", i64), ("sh", i64)]
+
+
 LIB_NAME = "libflowwarp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 if os.environ.get("FWB_LIB"):  # A/B hook: another build of the same library (e.g. different launch bounds)
@@ -117,6 +121,11 @@ SYMBOLS = (
     "fwb_workspace_bytes",
     "fwb_warp_blend_backward_flow",
     "fwb_warp_blend_backward_src",
+    "fwb_loss_partials_bytes",
+    "fwb_flowgrad_loss_forward",
+    "fwb_flowgrad_loss_backward",
+    "fwb_masked_abs_forward",
+    "fwb_masked_abs_backward",
 )
 
 _lib = None
@@ -168,6 +177,18 @@ def load() -> C.CDLL:
     lib.fwb_warp_blend_backward_flow.argtypes = [pp, gp, vp, C.c_size_t, vp]
     lib.fwb_warp_blend_backward_src.restype = C.c_int32
     lib.fwb_warp_blend_backward_src.argtypes = [pp, gp, vp, C.c_size_t, vp]
+    wp = C.POINTER(fwb_view)
+    i32 = C.c_int32
+    lib.fwb_loss_partials_bytes.restype = C.c_size_t
+    lib.fwb_loss_partials_bytes.argtypes = [i32, i32, i32]
+    lib.fwb_flowgrad_loss_forward.restype = i32
+    lib.fwb_flowgrad_loss_forward.argtypes = [wp, wp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.fwb_flowgrad_loss_backward.restype = i32
+    lib.fwb_flowgrad_loss_backward.argtypes = [wp, wp, i32, i32, i32, i32, i32, vp, wp, vp]
+    lib.fwb_masked_abs_forward.restype = i32
+    lib.fwb_masked_abs_forward.argtypes = [wp, wp, wp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.fwb_masked_abs_backward.restype = i32
+    lib.fwb_masked_abs_backward.argtypes = [wp, wp, wp, i32, i32, i32, i32, i32, vp, wp, wp, wp, vp]
     _lib = lib
     return lib
 

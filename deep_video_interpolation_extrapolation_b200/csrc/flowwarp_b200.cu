@@ -24,6 +24,7 @@
 #include "fwb_bwdx.cuh"
 #include "fwb_blend.cuh"
 #include "fwb_label.cuh"
+#include "fwb_loss.cuh"
 
 namespace fwb {
 
@@ -1128,6 +1129,82 @@ int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, vo
     return rc;
   }
   return run_backward_src(p, g, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// flow-regularisation losses (fwb_loss.cuh)
+// ---------------------------------------------------------------------------------------------
+static LossView to_view(const fwb_view* v) {
+  LossView o = {nullptr, 0, 0, 0, 0};
+  if (v && v->ptr) o = {v->ptr, v->sn, v->st, v->sc, v->sh};
+  return o;
+}
+static int32_t loss_dims_ok(int32_t N, int32_t T, int32_t C, int32_t H, int32_t W) {
+  if (N < 0 || T < 1 || C < 1 || H < 1 || W < 1) return FWB_E_SHAPE;
+  if ((long long)N * T > 65535 || H > 65535) return FWB_E_SHAPE;
+  return 0;
+}
+
+extern "C" {
+
+size_t fwb_loss_partials_bytes(int32_t N, int32_t T, int32_t H) {
+  if (N < 1 || T < 1 || H < 1) return sizeof(float2);
+  return (size_t)N * T * H * sizeof(float2);
+}
+
+int32_t fwb_flowgrad_loss_forward(const fwb_view* flow, const fwb_view* image, int32_t N, int32_t T, int32_t C, int32_t H,
+                                  int32_t W, void* partials, float* loss, void* stream) {
+  int32_t rc = loss_dims_ok(N, T, C, H, W);
+  if (rc) return rc;
+  if (!flow || !flow->ptr || !image || !image->ptr || !partials || !loss) return FWB_E_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 0) return (int32_t)cudaMemsetAsync(loss, 0, sizeof(float), s);
+  flowgrad_fwd_kernel<<<dim3(H, N * T), LS_THREADS, 0, s>>>(to_view(flow), to_view(image), T, C, H, W, (float2*)partials);
+  // per frame: mean over N*2*H*(W-1) and N*2*(H-1)*W elements; the frames are summed and divided by T
+  const double cx = (double)N * 2.0 * H * (W - 1), cy = (double)N * 2.0 * (H - 1) * W;
+  loss_final_kernel<<<1, LS_THREADS, 0, s>>>((const float2*)partials, (long long)N * T * H, cx > 0 ? 1.0 / (cx * T) : 0.0,
+                                             cy > 0 ? 1.0 / (cy * T) : 0.0, loss);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_flowgrad_loss_backward(const fwb_view* flow, const fwb_view* image, int32_t N, int32_t T, int32_t C, int32_t H,
+                                   int32_t W, const float* grad_loss, const fwb_view* grad_flow, void* stream) {
+  int32_t rc = loss_dims_ok(N, T, C, H, W);
+  if (rc) return rc;
+  if (!flow || !flow->ptr || !image || !image->ptr || !grad_loss || !grad_flow || !grad_flow->ptr) return FWB_E_NULL;
+  if (N == 0) return 0;
+  const double cx = (double)N * 2.0 * H * (W - 1), cy = (double)N * 2.0 * (H - 1) * W;
+  flowgrad_bwd_kernel<<<dim3((W + LS_THREADS - 1) / LS_THREADS, H, N * T), LS_THREADS, 0, (cudaStream_t)stream>>>(
+      to_view(flow), to_view(image), T, C, H, W, grad_loss, cx > 0 ? (float)(1.0 / (cx * T)) : 0.f, cy > 0 ? (float)(1.0 / (cy * T)) : 0.f,
+      grad_flow->ptr, grad_flow->sn, grad_flow->st, grad_flow->sc, grad_flow->sh);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_masked_abs_forward(const fwb_view* a, const fwb_view* b, const fwb_view* mask, int32_t N, int32_t T, int32_t C, int32_t H,
+                              int32_t W, void* partials, float* loss, void* stream) {
+  int32_t rc = loss_dims_ok(N, T, C, H, W);
+  if (rc) return rc;
+  if (!a || !a->ptr || !b || !b->ptr || !partials || !loss) return FWB_E_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 0) return (int32_t)cudaMemsetAsync(loss, 0, sizeof(float), s);
+  masked_l1_fwd_kernel<<<dim3(H, N * T), LS_THREADS, 0, s>>>(to_view(a), to_view(b), to_view(mask), T, C, H, W, (float2*)partials);
+  loss_final_kernel<<<1, LS_THREADS, 0, s>>>((const float2*)partials, (long long)N * T * H, 1.0 / ((double)N * C * H * W), 0.0, loss);
+  return (int32_t)cudaGetLastError();
+}
+
+int32_t fwb_masked_abs_backward(const fwb_view* a, const fwb_view* b, const fwb_view* mask, int32_t N, int32_t T, int32_t C, int32_t H,
+                               int32_t W, const float* grad_loss, const fwb_view* grad_a, const fwb_view* grad_b,
+                               const fwb_view* grad_mask, void* stream) {
+  int32_t rc = loss_dims_ok(N, T, C, H, W);
+  if (rc) return rc;
+  if (!a || !a->ptr || !b || !b->ptr || !grad_loss) return FWB_E_NULL;
+  if (N == 0) return 0;
+  masked_l1_bwd_kernel<<<dim3((W + LS_THREADS - 1) / LS_THREADS, H, N * T), LS_THREADS, 0, (cudaStream_t)stream>>>(
+      to_view(a), to_view(b), to_view(mask), T, C, H, W, grad_loss, (float)(1.0 / ((double)N * C * H * W)), to_view(grad_a), to_view(grad_b),
+      to_view(grad_mask));
+  return (int32_t)cudaGetLastError();
 }
 
 }  // extern "C"

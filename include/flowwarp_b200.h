@@ -180,6 +180,13 @@ typedef struct fwb_label_problem {
   int32_t _pad;
 } fwb_label_problem;
 
+/* A strided fp32 view [N,T,C,H,W] (element strides, W-stride 1) for the loss entry points: a frame slice flow[:, :, i] of the
+ * reference's [N,2,T,H,W] layout is a view with sc = the T*H*W plane stride and st = H*W: no copy. */
+typedef struct fwb_view {
+  float* ptr; /* NULL: tensor absent */
+  int64_t sn, st, sc, sh;
+} fwb_view;
+
 /* Library version (FWB_VERSION of the build). */
 int32_t fwb_version(void);
 
@@ -235,6 +242,26 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
  * Replaces the atomicAdd scatter of ATen grid_sampler_2d_backward. */
 int32_t fwb_warp_blend_backward_src(const fwb_problem* p, const fwb_grads* g, void* workspace,
                                     size_t workspace_bytes, void* stream);
+
+/* The flow-regularisation losses that consume the warp.  Their Python source is deleted from the reference;
+ * the formulas are read from the bytecode in __pycache__/losses.cpython-36.pyc and use utils/net_utils.py:243-248
+ * (gradientx / gradienty) and the FlowWrapper held as self.flowwarp (runners/VAEer.py:53):
+ *   TrainingLoss._flowgradloss (pyc line 413):  flow*128, image*256,  w = exp(-mean_c |grad(image)|),
+ *       loss = mean |gradientx(flow) * wx| + mean |gradienty(flow) * wy|, summed over the T frames of the views / T
+ *   TrainingLoss._flowconsist (pyc line 481):   mean(mask * |a - b|) with a = flowwarp(...) (this library's warp) per term
+ * partials: scratch of fwb_loss_partials_bytes(N, T, H) bytes; loss: one device float.  Deterministic (fixed-order sums). */
+size_t fwb_loss_partials_bytes(int32_t N, int32_t T, int32_t H);
+int32_t fwb_flowgrad_loss_forward(const fwb_view* flow /* C = 2 */, const fwb_view* image, int32_t N, int32_t T, int32_t C,
+                                  int32_t H, int32_t W, void* partials, float* loss, void* stream);
+/* gradient w.r.t. flow (the image is data); grad_loss: one device float */
+int32_t fwb_flowgrad_loss_backward(const fwb_view* flow, const fwb_view* image, int32_t N, int32_t T, int32_t C, int32_t H,
+                                   int32_t W, const float* grad_loss, const fwb_view* grad_flow, void* stream);
+/* loss = sum_t mean_{n,c,h,w}( mask * |a - b| ) (mask [N,T,1,H,W] view or NULL) */
+int32_t fwb_masked_abs_forward(const fwb_view* a, const fwb_view* b, const fwb_view* mask, int32_t N, int32_t T, int32_t C,
+                              int32_t H, int32_t W, void* partials, float* loss, void* stream);
+int32_t fwb_masked_abs_backward(const fwb_view* a, const fwb_view* b, const fwb_view* mask, int32_t N, int32_t T, int32_t C,
+                               int32_t H, int32_t W, const float* grad_loss, const fwb_view* grad_a, const fwb_view* grad_b,
+                               const fwb_view* grad_mask, void* stream);
 
 #ifdef __cplusplus
 }

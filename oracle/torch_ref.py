@@ -75,3 +75,44 @@ def ref_warp_blend(frames0, frames1, for_flow, back_flow, for_mask, back_mask, p
         wb = F.grid_sample(b, gb, mode="bilinear", padding_mode=padding_mode, align_corners=align_corners)
         outs.append(for_mask * wa + back_mask * wb)
     return outs
+
+
+# --------------------------------------------------------------------------------------------- flow-regularisation losses
+# The reference's losses.py is deleted; TrainingLoss._flowgradloss (pyc line 413) and TrainingLoss._flowconsist (pyc line 481)
+# are restated here from the bytecode in __pycache__/losses.cpython-36.pyc, on top of utils/net_utils.py:243-248.
+def ref_gradientx(img):
+    return img[:, :, :, :-1] - img[:, :, :, 1:]
+
+
+def ref_gradienty(img):
+    return img[:, :, :-1, :] - img[:, :, 1:, :]
+
+
+def ref_flowgradloss_frame(flow, image):
+    flow = flow * 128
+    image = image * 256
+    fx, fy = ref_gradientx(flow), ref_gradienty(flow)
+    wx = torch.exp(-torch.mean(torch.abs(ref_gradientx(image)), 1, keepdim=True))
+    wy = torch.exp(-torch.mean(torch.abs(ref_gradienty(image)), 1, keepdim=True))
+    return torch.mean(torch.abs(fx * wx)) + torch.mean(torch.abs(fy * wy))
+
+
+def ref_flowgradloss(flow, image, t):
+    """flow [N,2,T,H,W], image [N,T,C,H,W] (TrainingLoss.flowgradloss: sum over the frames / t)."""
+    s = 0.0
+    for i in range(t):
+        s = s + ref_flowgradloss_frame(flow[:, :, i], image[:, i])
+    return s / t
+
+
+def ref_flowconsist(flow, flowback, mask_fw, mask_bw, t, align_corners=False):
+    """TrainingLoss.flowconsist: sum over the frames of prev + next (masks only when both are given)."""
+    s = 0.0
+    for i in range(t):
+        f, b = flow[:, :, i], flowback[:, :, i]
+        prev = torch.abs(ref_flow_wrapper(f, -b, align_corners) - b)
+        nxt = torch.abs(ref_flow_wrapper(b, f, align_corners) - f)
+        if mask_fw is not None and mask_bw is not None:
+            prev, nxt = mask_bw[:, i:i + 1] * prev, mask_fw[:, i:i + 1] * nxt
+        s = s + prev.mean() + nxt.mean()
+    return s

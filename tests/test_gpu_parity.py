@@ -881,3 +881,45 @@ def test_caller_expanded_source_keeps_per_frame_gradient(pkg, oracle):
         out.backward(cu(go))
         rg = oracle.backward([x], [fl], [go], gates=[m])
         assert relerr(xt.grad, rg["grad_srcs"][0][0].sum(axis=1)) <= BWD_TOL
+
+
+# ---------------------------------------------------------------- flow-regularisation losses
+LOSS_TOL = 2e-6
+
+
+@pytest.mark.parametrize("name", ["losses_0.npz", "losses_1.npz", "losses_2.npz"])
+@pytest.mark.parametrize("det", [False, True])
+def test_flow_losses_vs_reference_golden(pkg, golden_dir, name, det):
+    """flowgradloss / flowconsist (the library's warp kernels + the fused reductions of csrc/fwb_loss.cuh) against goldens made
+    with the reference's own FlowWrapper / gradientx / gradienty composed in the order of the surviving bytecode."""
+    from test_oracle_golden import _loss_inputs
+    z = np.load(os.path.join(golden_dir, name))
+    T, flow, flowback, image, m_fw, m_bw = _loss_inputs(z)
+    tf, tb, ti = cu(flow, True), cu(flowback, True), cu(image)
+    assert np.array_equal(pkg.gradientx(ti[:, 0]).cpu().numpy(), z["gx"]) and np.array_equal(pkg.gradienty(ti[:, 0]).cpu().numpy(), z["gy"])
+    lg = pkg.flowgradloss(tf, ti, T)
+    lg.backward()
+    assert abs(float(lg) - float(z["flowgrad"])) <= LOSS_TOL * abs(float(z["flowgrad"]))
+    assert relerr(tf.grad, z["flowgrad_gflow"]) <= BWD_TOL
+    # one frame through the 4-D entry point == the frame loop's term
+    l1 = pkg.flow_gradient_loss(cu(flow[:, :, 0]), ti[:, 0])
+    ref1 = pkg.flowgradloss(cu(flow[:, :, :1]), ti[:, :1], 1)
+    assert float(l1) == float(ref1)
+    tf.grad = None
+    tm = [None if m is None else cu(m, True) for m in (m_fw, m_bw)]
+    fw = pkg.FlowWrapper(deterministic=det)
+    lc = pkg.flowconsist(fw, tf, tb, tm[0], tm[1], T)
+    lc.backward()
+    assert abs(float(lc) - float(z["flowcon"])) <= LOSS_TOL * abs(float(z["flowcon"]))
+    assert relerr(tf.grad, z["flowcon_gflow"]) <= BWD_TOL and relerr(tb.grad, z["flowcon_gflowback"]) <= BWD_TOL
+    if tm[0] is not None:
+        assert relerr(tm[0].grad, z["flowcon_gmfw"]) <= BWD_TOL and relerr(tm[1].grad, z["flowcon_gmbw"]) <= BWD_TOL
+
+
+def test_flow_losses_are_deterministic_and_reject_cpu(pkg):
+    N, T, H, W = 2, 2, 33, 50
+    f, img = cu(synth.flow(1, N, H, W, 3.0, T=T), True), cu(np.stack([synth.mask(5 + c, N, H, W, T=T) for c in range(3)], 2))
+    a = [float(pkg.flowgradloss(f, img, T)) for _ in range(3)]
+    assert a[0] == a[1] == a[2]
+    with pytest.raises(RuntimeError):
+        pkg.flowgradloss(f.cpu(), img.cpu(), T)

@@ -153,3 +153,38 @@ def test_flat_entry_matches_struct_entry_and_torch(oracle, pad, align):
         assert relerr(flat["out"][g], outs[g].detach().numpy()) <= 1e-6
         assert relerr(flat["gsrc0"][g], a0[g].grad.numpy()) <= 1e-5 and relerr(flat["gsrc1"][g], a1[g].grad.numpy()) <= 1e-5
     assert relerr(flat["gflow0"], tff.grad.numpy()) <= 1e-5 and relerr(flat["gblend1"], tmb.grad.numpy()[:, 0]) <= 1e-5
+
+
+# ---------------------------------------------------------------- flow-regularisation losses
+def _loss_inputs(z):
+    N, T, C, H, W = z["shape"]
+    s = z["seeds"]
+    flow = synth.flow(s[0], N, H, W, 3.0, T=T)
+    flowback = synth.flow(s[1], N, H, W, 3.0, T=T)
+    image = np.stack([2 * synth.mask(s[2] + 100 * c, N, H, W, T=T) - 1 for c in range(C)], 2)
+    masks = bool(z["masks"])
+    m_fw = synth.mask(s[3], N, H, W, T=T) if masks else None
+    m_bw = synth.mask(s[4], N, H, W, T=T) if masks else None
+    return int(T), flow, flowback, image, m_fw, m_bw
+
+
+@pytest.mark.parametrize("name", ["losses_0.npz", "losses_1.npz", "losses_2.npz"])
+def test_flow_losses_restatement_vs_reference_golden(golden_dir, name):
+    """oracle/torch_ref.py's restatement of TrainingLoss.flowgradloss / flowconsist against the goldens made with the reference's
+    own FlowWrapper / gradientx / gradienty (tests/golden/make_golden_losses.py)."""
+    z = np.load(os.path.join(golden_dir, name))
+    T, flow, flowback, image, m_fw, m_bw = _loss_inputs(z)
+    tf, tb = torch.from_numpy(flow).requires_grad_(), torch.from_numpy(flowback).requires_grad_()
+    ti = torch.from_numpy(image)
+    assert np.array_equal(torch_ref.ref_gradientx(ti[:, 0]).numpy(), z["gx"]) and np.array_equal(torch_ref.ref_gradienty(ti[:, 0]).numpy(), z["gy"])
+    lg = torch_ref.ref_flowgradloss(tf, ti, T)
+    lg.backward()
+    assert abs(float(lg) - float(z["flowgrad"])) <= 1e-6 * abs(float(z["flowgrad"]))
+    assert np.abs(tf.grad.numpy() - z["flowgrad_gflow"]).max() <= 1e-6 * np.abs(z["flowgrad_gflow"]).max()
+    tf.grad = None
+    tm = [None if m is None else torch.from_numpy(m).requires_grad_() for m in (m_fw, m_bw)]
+    lc = torch_ref.ref_flowconsist(tf, tb, tm[0], tm[1], T)
+    lc.backward()
+    assert abs(float(lc) - float(z["flowcon"])) <= 1e-6 * abs(float(z["flowcon"]))
+    assert np.abs(tf.grad.numpy() - z["flowcon_gflow"]).max() <= 1e-5 * np.abs(z["flowcon_gflow"]).max()
+    assert np.abs(tb.grad.numpy() - z["flowcon_gflowback"]).max() <= 1e-5 * np.abs(z["flowcon_gflowback"]).max()
