@@ -592,9 +592,18 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
     pipe = P.HostWarpBlend(dev, chunk=args.e2e_chunk, padding_mode="border", deterministic=args.deterministic)
     G = len(inp["f0"])
 
-    def e2e_step():
-        pipe.run(host_in[:G], host_in[G:2 * G], host_in[2 * G], host_in[2 * G + 1], host_in[2 * G + 2], host_in[2 * G + 3],
-                 host_in[2 * G + 4:], synchronize=False)
+    # the producer (data loader / previous stage) writes its tensors straight into the pinned per-chunk ARENAS, so every chunk
+    # moves with ONE cudaMemcpyAsync each way (HostWarpBlend.arena / run_arena); --e2e-per-tensor times the 13 + 11 copies path
+    if args.e2e_per_tensor:
+        def e2e_step():
+            pipe.run(host_in[:G], host_in[G:2 * G], host_in[2 * G], host_in[2 * G + 1], host_in[2 * G + 2], host_in[2 * G + 3],
+                     host_in[2 * G + 4:], synchronize=False)
+    else:
+        pipe.fill_arena(host_in[:G], host_in[G:2 * G], host_in[2 * G], host_in[2 * G + 1], host_in[2 * G + 2], host_in[2 * G + 3],
+                        host_in[2 * G + 4:])
+
+        def e2e_step():
+            pipe.run_arena(synchronize=False)
 
     e2e_steps = max(3, min(args.steps, 10))
     e2e_el = sharding.max_over_ranks(timed(e2e_step, e2e_steps, 2, sync), dev)
@@ -643,8 +652,10 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             "kernels": kernels,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "chunk": args.e2e_chunk, "numa_local_cores": numa_cores,
-                    "api": "deep_video_interpolation_extrapolation_b200.HostWarpBlend.run (forward + backward C-ABI calls per batch chunk; "
-                           "pinned host in/out, H2D | compute | D2H on three streams)"},
+                    "h2d_GBps": h2d * e2e_steps / e2e_el / 1e9, "d2h_GBps": d2h * e2e_steps / e2e_el / 1e9,
+                    "copies_per_chunk": "13 + 11 (per tensor)" if args.e2e_per_tensor else "1 + 1 (pinned arenas)",
+                    "api": ("deep_video_interpolation_extrapolation_b200.HostWarpBlend." + ("run" if args.e2e_per_tensor else "run_arena")
+                            + " (forward + backward C-ABI calls per batch chunk; pinned host in/out, H2D | compute | D2H on three streams)")},
             "gpu_launches": args.steps * launches,
             "clocks": clocks,
         }
@@ -692,7 +703,8 @@ def main():
     ap.add_argument("--zero", default="fwd", choices=["fwd", "memset", "side"],
                     help="who zero-fills grad_src before the fused backward: the forward kernel (default), the backward's "
                          "memsets, or a side stream (A/B)")
-    ap.add_argument("--e2e-chunk", type=int, default=2, help="clips per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--e2e-chunk", type=int, default=1, help="clips per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--e2e-per-tensor", action="store_true", help="e2e leg with one copy per tensor instead of the pinned arenas")
     ap.add_argument("--aux", action="store_true", help="also time the mask-blend (refine) kernels")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -504,6 +504,30 @@ def test_host_pipeline_matches_oracle_and_device_op(pkg, oracle, chunk):
         pipe.run([cu(a) for a in f0], [h(a) for a in f1], h(ff), h(fb), h(mf), h(mb), [h(g) for g in gos])
 
 
+@pytest.mark.parametrize("chunk", [1, 2, 8])
+def test_host_pipeline_arena_mode_matches_oracle(pkg, oracle, chunk):
+    """HostWarpBlend.arena / fill_arena / run_arena: every chunk moves with ONE copy each way out of / into pinned arenas whose
+    per-chunk views the producer writes directly; same results as the oracle (ragged last chunk: N=5)."""
+    N, H, W = 5, 40, 64
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    ref = oracle.forward(list(zip(f0, f1)), [ff, fb], blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    pipe = pkg.HostWarpBlend("cuda:0", chunk=chunk)
+    a = pipe.fill_arena([t(x) for x in f0], [t(x) for x in f1], t(ff), t(fb), t(mf), t(mb), [t(g) for g in gos])
+    for _ in range(2):
+        pipe.run_arena()
+    G = len(f0)
+    cat = lambda k: torch.cat([views[k] for views in a["results"]], 0)  # noqa: E731  (chunk views -> the whole batch)
+    for g in range(G):
+        assert relerr(cat(g), ref[g][:, 0]) <= FWD_TOL
+        assert relerr(cat(G + g), rg["grad_srcs"][g][0][:, 0]) <= BWD_TOL
+        assert relerr(cat(2 * G + g), rg["grad_srcs"][g][1][:, 0]) <= BWD_TOL
+    assert relerr(cat(3 * G), rg["grad_flows"][0][:, :, 0]) <= BWD_TOL and relerr(cat(3 * G + 1), rg["grad_flows"][1][:, :, 0]) <= BWD_TOL
+    assert relerr(cat(3 * G + 2), rg["grad_blends"][0]) <= BWD_TOL and relerr(cat(3 * G + 3), rg["grad_blends"][1]) <= BWD_TOL
+    assert len(a["chunks"]) == (N + min(chunk, N) - 1) // min(chunk, N)
+
+
 # ---------------------------------------------------------------- grad_src zero-fill fused into the forward
 @pytest.mark.parametrize("shape,sigma,T", [((2, 48, 64), 8.0, 1), ((1, 37, 52), 8.0, 1), ((1, 33, 50), 8.0, 1),
                                            ((1, 64, 96), 300.0, 1), ((2, 40, 64), 6.0, 3)])
