@@ -44,11 +44,20 @@ KERNEL_BYTES = {"forward": 12 * C_TOTAL + 24, "backward_flow": 12 * C_TOTAL + 48
 
 def config_dict(cfg, args, world):
     """The `config` object of the JSON line: identical keys in the b200 and the reference arm."""
-    return {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
+    d = {"workload": cfg["name"], "per_gpu_batch": cfg["N"], "H": cfg["H"], "W": cfg["W"], "channels": list(CH),
             "flow_sigma_px": cfg["sigma"], "chained_steps": cfg["chain"], "padding_mode": "border", "align_corners": False,
             "forward_only": bool(cfg.get("fwd_only", False)),
             "parallelism": f"batch-sharded x{world}, no collective in the op",
             "l2": "inputs+outputs per step (~1.2 GB at config 2) exceed the 126 MB L2; no explicit flush"}
+    fused = not (args.deterministic or getattr(args, "atomic_src", False))
+    d.update({"deterministic": bool(args.deterministic),
+              "grad_src_zeroing": args.zero if (fused and not cfg.get("fwd_only", False)) else "memset"})
+    if cfg["chain"] > 1:
+        d["chain"] = ("true K-step chain through the autograd op: prediction k is a source of step k+1, seg re-one-hotted "
+                      "by argmax, gradient through the RGB prediction, one backward (runners/ExtraTrainer.py:254-310)")
+    if cfg["allreduce"]:
+        d["allreduce"] = f"{cfg['allreduce']} fp32 parameters, dist.all_reduce(async_op=True) issued before the op, joined after it"
+    return d
 
 
 def ncu_traffic(kernel, cfg_id):
@@ -217,7 +226,7 @@ def run_reference_arm(args, cfg, rank, world):
         "impl": "reference", "metric": "warp+blend fwd+bwd Gpix/s", "value": val, "unit": "Gpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(cfg, args, args.gpus),
+        "config": config_dict(cfg, args, args.gpus),  # the same keys and values as the b200 arm
         "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample,
                          "what": "oracle/torch_ref.py: the reference's own torch-op sequence (utils/net_utils.py:93-114, "
                                  "nets/OpticalUnet.py:123-146) restated; the reference has no installable package (no setup.py)"},
@@ -630,12 +639,6 @@ def run_b200_arm(args, cfg, rank, local_rank, world):
             step_bytes = BYTES_PER_PIX
         step_gbs = value / world * step_bytes  # per-GPU Gpix/s * B/pix = GB/s
         cfgd = config_dict(cfg, args, world)
-        cfgd.update({"deterministic": bool(args.deterministic), "grad_src_zeroing": step.zero})
-        if chain > 1:
-            cfgd["chain"] = ("true K-step chain through the autograd op: prediction k is a source of step k+1, seg re-one-hotted "
-                             "by argmax, gradient through the RGB prediction, one backward (runners/ExtraTrainer.py:254-310)")
-        if ar_buf is not None:
-            cfgd["allreduce"] = f"{cfg['allreduce']} fp32 parameters, dist.all_reduce(async_op=True) issued before the op, joined after it"
         launches = (1 if fwd_only else (LAUNCHES_PER_STEP["fused"] if step.fused else LAUNCHES_PER_STEP["split"]))
         if chain > 1:  # per chain: step 0 (frames are data) forward + kernel 2; later steps forward (zero-fill) + fused backward
             launches = 2 * chain
