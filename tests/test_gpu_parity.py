@@ -315,7 +315,7 @@ def test_deterministic_mode_bit_exact_run_to_run(pkg):
 
 
 # ---------------------------------------------------------------- every kernel variant stays parity-checked
-VARIANTS = ["", "sorted", "notex", "notile", "notex,notile", "generic,nofuse", "nofuse"]
+VARIANTS = ["", "nocl", "sorted", "notex", "notile", "notex,notile", "generic,nofuse", "nofuse"]
 
 
 @pytest.mark.parametrize("det", [False, True])
@@ -947,3 +947,61 @@ def test_flow_losses_are_deterministic_and_reject_cpu(pkg):
     assert a[0] == a[1] == a[2]
     with pytest.raises(RuntimeError):
         pkg.flowgradloss(f.cpu(), img.cpu(), T)
+
+
+# ---------------------------------------------------------------- the channel-per-lane fused backward (csrc/fwb_cl.cuh)
+@pytest.mark.parametrize("Cs,D,T,shape,sigma,pad", [
+    ([12], 1, 1, (2, 40, 64), 8.0, "zeros"),       # the narrowest channel set that takes the kernel, one direction
+    ([31], 2, 1, (1, 37, 52), 8.0, "border"),      # every lane but the tap counter's, ragged tiles
+    ([3, 20], 2, 3, (1, 48, 96), 6.0, "zeros"),    # T frames, shared source (summed gradient), two groups
+    ([3, 20], 2, 1, (1, 64, 128), 60.0, "border"),  # large displacements: many slow items (owner-thread scatter)
+    ([23], 1, 2, (2, 33, 68), 300.0, "zeros"),     # nearly every tap outside the image
+    ([5, 9], 2, 1, (2, 16, 32), 2.0, "border"),    # tiles smaller than 32x8 in both dimensions of the grid
+])
+def test_channel_lane_backward_vs_oracle(pkg, oracle, Cs, D, T, shape, sigma, pad):
+    N, H, W = shape
+    signs = [-1.0, 1.0][:D]
+    srcs = [[synth.rgb(300 + 10 * g + d, N, H, W, C)[:, None] for d in range(D)] for g, C in enumerate(Cs)]
+    flows = [synth.flow(310 + d, N, H, W, sigma, T=T, oob_frac=0.02) for d in range(D)]
+    gates = [synth.mask(320 + d, N, H, W, T=T) for d in range(D)]
+    blends = [synth.mask(330 + d, N, H, W, T=T) for d in range(D)]
+    gos = [synth.grad(340 + g, (N, T, C, H, W)) for g, C in enumerate(Cs)]
+    osrc = [tuple(np.broadcast_to(x, (N, T) + x.shape[2:]) for x in row) for row in srcs]
+    ref = oracle.forward(osrc, flows, gates=gates, blends=blends, signs=signs, padding_mode=pad)
+    rg = oracle.backward(osrc, flows, gos, gates=gates, blends=blends, signs=signs, padding_mode=pad)
+    ts = [[cu(x, True) for x in row] for row in srcs]
+    tf, tg, tb = [cu(f, True) for f in flows], [cu(g, True) for g in gates], [cu(b, True) for b in blends]
+    outs = pkg.flow_warp_blend([tuple(r) for r in ts], tf, gates=tg, blends=tb, signs=signs, padding_mode=pad)
+    torch.autograd.backward(outs, [cu(g) for g in gos])
+    for g in range(len(Cs)):
+        assert relerr(outs[g], ref[g]) <= FWD_TOL
+        for d in range(D):
+            want = rg["grad_srcs"][g][d]
+            assert relerr(ts[g][d].grad, want.sum(axis=1, keepdims=True) if want.shape[1] != 1 else want) <= BWD_TOL
+    for d in range(D):
+        assert relerr(tf[d].grad, rg["grad_flows"][d]) <= BWD_TOL
+        assert relerr(tg[d].grad, rg["grad_gates"][d]) <= BWD_TOL and relerr(tb[d].grad, rg["grad_blends"][d]) <= BWD_TOL
+
+
+def test_channel_lane_backward_non_finite_and_partial_gradients(pkg, oracle):
+    """inf / NaN in grad_out of two of 16 channels: those channels take the exact float path (the non-finite value reaches grad_src as
+    in the reference), the others stay finite and correct; and a source gradient wanted for one direction only."""
+    N, H, W, C = 1, 40, 64, 16
+    x0, x1 = synth.rgb(1, N, H, W, C), synth.rgb(2, N, H, W, C)
+    ff, fb = synth.flow(3, N, H, W, 4.0, oob_frac=0.0), synth.flow(4, N, H, W, 4.0, oob_frac=0.0)
+    go = synth.grad(5, (N, C, H, W))
+    t0, t1 = cu(x0, True), cu(x1, False)  # gradient for direction 0 only
+    tff, tfb = cu(ff, True), cu(fb, True)
+    gt = cu(go).clone()
+    gt[0, 3, 10, 20] = float("inf")
+    gt[0, 7, 5, 9] = float("nan")
+    out = pkg.flow_warp_blend([(t0, t1)], [tff, tfb], signs=[-1.0, 1.0], padding_mode="border")[0]
+    out.backward(gt)
+    assert t1.grad is None
+    g = t0.grad
+    assert torch.isinf(g[0, 3]).any() and torch.isnan(g[0, 7]).any()
+    rg = oracle.backward([(x0[:, None], x1[:, None])], [ff[:, :, None], fb[:, :, None]], [go[:, None]], signs=[-1.0, 1.0], padding_mode="border")
+    want = rg["grad_srcs"][0][0][:, 0]
+    ok = [c for c in range(C) if c not in (3, 7)]
+    assert torch.isfinite(g[0, ok]).all()
+    assert relerr(g[:, ok], want[:, ok]) <= BWD_TOL
