@@ -82,15 +82,20 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
   }
   const bool in = j < G.W && i < G.H;
 #if TXF_ZERO_FIRST
-  if (Z.on) {  // 64 float4 per plane and tile: a quarter of the CTA per plane, planes round robin
+  if (Z.on) {  // 64 float4 per plane and tile: a quarter of the CTA per plane, the planes of a (group, direction) round robin
     const int f4 = threadIdx.x & 63, zi = blockIdx.y * TXF_TH + (f4 >> 3), zj = blockIdx.x * TXF_TW + (f4 & 7) * 4;
     if (zi < G.H && zj < G.W) {
-      for (int pl = threadIdx.x >> 6; pl < Ctot * NDIRS; pl += TXF_THREADS / 64) {
-        const int cf = pl / NDIRS, d = pl - cf * NDIRS;
-        int g, c;
-        chan_lookup(P, cf, g, c);
-        float* zp = zero_plane(Z, G, g, d, n, t, c);
-        if (zp) *reinterpret_cast<float4*>(zp + (long long)zi * Z.sh[d] + zj) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < G.n_groups; ++g) {
+        const int C = P.grp[g].C;
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d) {
+          float* zp = Z.gs[g][d];
+          if (!zp || (t != 0 && Z.st[g][d] == 0)) continue;  // a source shared by all T frames is cleared by the t == 0 tiles
+          zp += n * Z.sn[g][d] + t * Z.st[g][d] + (long long)zi * Z.sh[d] + zj;
+          const long long sc = Z.sc[g][d];
+          for (int c = threadIdx.x >> 6; c < C; c += TXF_THREADS / 64) *reinterpret_cast<float4*>(zp + c * sc) = z4;
+        }
       }
     }
   }
