@@ -34,6 +34,9 @@
  *        gx      = sign < 0 ? bx - f : bx + f
  *        ix      = align_corners ? ((gx+1)/2)*(W-1) : fma(gx+1, W, -1)/2
  *        border  : ix = min(W-1, max(ix, 0));  non-finite or out-of-int-range -> -100
+ *                  (a NaN flow under border padding samples at coordinate 0 in the forward, as ATen's forward does; the backward
+ *                  keeps those taps, whereas ATen's backward sends the NaN coordinate to -100 and returns zero gradients there:
+ *                  a known deviation for NaN flows only)
  *        x0      = floor(ix); taps (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1); valid bit per tap = in image
  *        out[c]  = sum_d  blend_d * ( v_nw*nw + v_ne*ne + v_sw*sw + v_se*se )   in that order
  */
