@@ -1208,3 +1208,15 @@ int32_t fwb_masked_abs_backward(const fwb_view* a, const fwb_view* b, const fwb_
 }
 
 }  // extern "C"
+
+#ifdef CL_PROF
+// debug build only: phase timeline of bwd_cl_kernel (64 clock sums), cleared after reading
+extern "C" int fwb_debug_cl_prof(unsigned long long* out64) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyFromSymbol(out64, fwb::cl_prof_acc, sizeof(unsigned long long) * 64);
+  if (e != cudaSuccess) return (int)e;
+  static unsigned long long z[64];
+  return (int)cudaMemcpyToSymbol(fwb::cl_prof_acc, z, sizeof(z));
+}
+#endif

@@ -36,6 +36,9 @@ constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the st
 #ifndef CL_CB_N
 #define CL_CB_N 1
 #endif
+#ifndef CL_PATCH
+#define CL_PATCH 1  // 1: a pixel warp covers an 8 x 4 patch of the tile; 0: a 32 x 1 row (A/B: no difference, 0.559 vs 0.563 ms)
+#endif
 #ifndef CL_DBG
 #define CL_DBG 0  // 2: the channel role returns after staging grad_out (timing experiment: the pixel role alone)
 #endif
@@ -44,6 +47,24 @@ constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the st
 #define CL_REGS_K3 0
 #endif
 constexpr int CL_CB = CL_CB_N;                 // channels per batch of texture fetches in kernel 2
+
+// -DCL_PROF: phase timeline of the kernel (clock64 deltas of the first thread of each role, summed over the CTAs; read back and
+// cleared by fwb_debug_cl_prof, tools/cl_prof.py).  Slots 0.. pixel role, 16.. channel role.
+#ifdef CL_PROF
+__device__ unsigned long long cl_prof_acc[64];
+#define CL_T0() long long cl_tprev = clock64()
+#define CL_T(idx)                                                                  \
+  do {                                                                             \
+    if ((threadIdx.x & 255) == 0) {                                                \
+      const long long now_ = clock64();                                            \
+      atomicAdd(&cl_prof_acc[idx], (unsigned long long)(now_ - cl_tprev));         \
+      cl_tprev = now_;                                                             \
+    }                                                                              \
+  } while (0)
+#else
+#define CL_T0()
+#define CL_T(idx)
+#endif
 
 struct ClChan {  // per flattened channel (groups that have a grad_out)
   float* gs[2];  // grad_src plane of (n, t, c) per direction, or NULL
@@ -209,6 +230,68 @@ __device__ __forceinline__ void cl_taps(const Params& P, int n, int t, int ic, i
 }
 
 
+// kernel 2's channel loop of one group: A_k += grad_out_c * tap_k,c for the quads of channel c in every direction.  The fetches
+// of channel c + 1 travel while those of channel c are summed (2 .. 4 TLD4 in flight per thread).
+template <int NDIRS>
+struct ClK2 {
+  unsigned long long th[NDIRS];
+  float fx1[NDIRS], row[NDIRS];  // fetch coordinates; row advances by H per channel (integers below 2^24: exact)
+  float fH;
+  const float* gq;  // staged grad_out of this pixel, channel stride CL_GS
+};
+template <int NDIRS>
+__device__ __forceinline__ void cl_k2_fetch(ClK2<NDIRS>& L, float4 (&q)[NDIRS]) {
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    q[d] = tex2Dgather<float4>((cudaTextureObject_t)L.th[d], L.fx1[d], L.row[d], 0);
+    L.row[d] += L.fH;
+  }
+}
+template <int NDIRS, bool MASKED>
+__device__ __forceinline__ void cl_k2_acc(const float4 (&q)[NDIRS], float gv, float (&A)[NDIRS][4], const unsigned (&m)[NDIRS][4]) {
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) {
+    // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
+    float a = q[d].w, b = q[d].z, c = q[d].x, e = q[d].y;
+    if (MASKED) {  // a tap outside the image counts as the value 0
+      a = __uint_as_float(__float_as_uint(a) & m[d][0]);
+      b = __uint_as_float(__float_as_uint(b) & m[d][1]);
+      c = __uint_as_float(__float_as_uint(c) & m[d][2]);
+      e = __uint_as_float(__float_as_uint(e) & m[d][3]);
+    }
+    A[d][0] = fmaf(gv, a, A[d][0]);
+    A[d][1] = fmaf(gv, b, A[d][1]);
+    A[d][2] = fmaf(gv, c, A[d][2]);
+    A[d][3] = fmaf(gv, e, A[d][3]);
+  }
+}
+template <int NDIRS, bool MASKED>
+__device__ __forceinline__ void cl_k2_group(ClK2<NDIRS>& L, int C, float (&A)[NDIRS][4], const unsigned (&m)[NDIRS][4]) {
+  // (a rolling window of 4 channels, 8 TLD4 in flight per thread, was measured: kernel 2's phase shrinks from 38 K to 30 K
+  // cycles per tile, the channel role's phases grow by as much - the two roles share the L1TEX data path - and the kernel
+  // takes 0.567 instead of 0.532 ms)
+  float4 qa[NDIRS], qb[NDIRS];
+  const float* gq = L.gq;
+  cl_k2_fetch<NDIRS>(L, qa);
+  int c = 0;
+#pragma unroll 1
+  for (; c + 2 < C; c += 2) {
+    cl_k2_fetch<NDIRS>(L, qb);
+    cl_k2_acc<NDIRS, MASKED>(qa, gq[0], A, m);
+    cl_k2_fetch<NDIRS>(L, qa);
+    cl_k2_acc<NDIRS, MASKED>(qb, gq[CL_GS], A, m);
+    gq += 2 * CL_GS;
+  }
+  if (C - c == 2) {
+    cl_k2_fetch<NDIRS>(L, qb);
+    cl_k2_acc<NDIRS, MASKED>(qa, gq[0], A, m);
+    cl_k2_acc<NDIRS, MASKED>(qb, gq[CL_GS], A, m);
+  } else {
+    cl_k2_acc<NDIRS, MASKED>(qa, gq[0], A, m);
+  }
+  L.gq += C * CL_GS;
+}
+
 struct ClSlow {  // a SLOW item with its taps (the first CL_SLOWCAP of a tile; the rest are scattered by their owner threads)
   float w[4];   // bilinear weights * blend
   int goff;     // y0 * row stride + x0 inside a grad_src plane
@@ -255,8 +338,15 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   const Geo& G = P.geo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pw = warp & 7, pp = (pw << 5) | lane;  // the pixel this thread owns
+  // a pixel warp is one 32 x 1 row of the tile: coalesced grad_out staging, conflict-free reads of the staged tile in kernel 2,
+  // x-consecutive items in the scatter (the texture rate does not depend on the patch shape)
+#if CL_PATCH
   const int j = blockIdx.x * CL_TW + (pw & 3) * 8 + (lane & 7);
   const int i = blockIdx.y * CL_TH + (pw >> 2) * 4 + (lane >> 3);
+#else
+  const int j = blockIdx.x * CL_TW + lane;
+  const int i = blockIdx.y * CL_TH + pw;
+#endif
   const int i0 = blockIdx.y * CL_TH;
   int n, t;
   if (G.T == 1) {
@@ -278,8 +368,10 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
 #if CL_REGS_K2
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CL_REGS_K2));
 #endif
+    CL_T0();
     ClTaps<NDIRS> k;
     cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic, jc, inimg, k);
+    CL_T(0);
     unsigned slowbits = 0u;
     {
       // ---- footprint tables and item descriptors of the scatter (thread = pixel; barrier 1 = the 8 pixel warps)
@@ -376,7 +468,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         oo[d * CL_NPIX + pp] = o;
       }
     }
+    CL_T(1);
     __syncthreads();  // descriptors and tables -> channel role; the staged grad_out tile -> kernel 2
+    CL_T(2);
     // ---- kernel 2 on the texture units
     // gix = sum_c gw_c [uy (b_c - a_c) + ty (d_c - c_c)] etc. (ATen grid_sampler_2d_backward): the weights do not depend on the
     // channel, so only the four sums  A_k = sum_c grad_out_c * tap_k,c  are accumulated per (pixel, direction) - one TLD4 and
@@ -393,70 +487,41 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     float A[NDIRS][4];
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) A[d][0] = A[d][1] = A[d][2] = A[d][3] = 0.0f;
-    const float fH = (float)G.H;
-    const float* gq = gos + pp;
-    for (int g = 0; g < G.n_groups; ++g) {
-      if (!Q.grad_out[g]) continue;
-      const int C = P.grp[g].C;
-      unsigned long long th[NDIRS];
-      float row0[NDIRS];
+    {
+      ClK2<NDIRS> L;
+      L.fH = (float)G.H;
+      L.gq = gos + pp;
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        const TexSrc& S = X.s[g][d];
-        const int blk = n / S.nb;
-        th[d] = S.tex[blk];
-        row0[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+      for (int d = 0; d < NDIRS; ++d) L.fx1[d] = fx1[d];
+      unsigned m[NDIRS][4];
+      if (masked) {
+#pragma unroll
+        for (int d = 0; d < NDIRS; ++d)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[d][q] = (k.vld[d] >> q) & 1u ? 0xffffffffu : 0u;
       }
-      auto acc4 = [&](const float4& q, float gv, int d) {
-        // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
-        if (masked) {
-          const unsigned v = k.vld[d];
-          A[d][0] = fmaf(gv, (v & 1u) ? q.w : 0.0f, A[d][0]);
-          A[d][1] = fmaf(gv, (v & 2u) ? q.z : 0.0f, A[d][1]);
-          A[d][2] = fmaf(gv, (v & 4u) ? q.x : 0.0f, A[d][2]);
-          A[d][3] = fmaf(gv, (v & 8u) ? q.y : 0.0f, A[d][3]);
-        } else {
-          A[d][0] = fmaf(gv, q.w, A[d][0]);
-          A[d][1] = fmaf(gv, q.z, A[d][1]);
-          A[d][2] = fmaf(gv, q.x, A[d][2]);
-          A[d][3] = fmaf(gv, q.y, A[d][3]);
-        }
-      };
-      // the quads of channel c + 1 travel while those of channel c are summed
-      float4 qa[NDIRS], qb[NDIRS];
-      float row[NDIRS];
+      for (int g = 0; g < G.n_groups; ++g) {
+        if (!Q.grad_out[g]) continue;
 #pragma unroll
-      for (int d = 0; d < NDIRS; ++d) {
-        row[d] = row0[d];
-        qa[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
+        for (int d = 0; d < NDIRS; ++d) {
+          const TexSrc& S = X.s[g][d];
+          const int blk = n / S.nb;
+          L.th[d] = S.tex[blk];
+          L.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+        }
+        if (masked)
+          cl_k2_group<NDIRS, true>(L, P.grp[g].C, A, m);
+        else
+          cl_k2_group<NDIRS, false>(L, P.grp[g].C, A, m);
       }
-#pragma unroll 1
-      for (int c = 0; c < C; c += 2) {
-        const bool more1 = c + 1 < C, more2 = c + 2 < C;
-        if (more1) {
-#pragma unroll
-          for (int d = 0; d < NDIRS; ++d) {
-            row[d] += fH;  // integers below 2^24: exact
-            qb[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
-          }
-        }
-        const float g0v = gq[c * CL_GS];
-#pragma unroll
-        for (int d = 0; d < NDIRS; ++d) acc4(qa[d], g0v, d);
-        if (more2) {
-#pragma unroll
-          for (int d = 0; d < NDIRS; ++d) {
-            row[d] += fH;
-            qa[d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d], 0);
-          }
-        }
-        if (more1) {
-          const float g1v = gq[(c + 1) * CL_GS];
-#pragma unroll
-          for (int d = 0; d < NDIRS; ++d) acc4(qb[d], g1v, d);
-        }
-      }
-      gq += C * CL_GS;
+    }
+    CL_T(3);
+    // the taps are recomputed for the epilogue (flow / mask reloads hit the L1): nothing but the fetch coordinates and the four
+    // sums per direction lives across the channel loop, which keeps it free of spills and rematerialised address arithmetic
+    {
+      int ic2 = ic, jc2 = jc;
+      asm volatile("" : "+r"(ic2), "+r"(jc2));
+      cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic2, jc2, inimg, k);
     }
     if (inimg) {
       // coordinate gradient -> grad_flow / grad_gate / grad_blend.  The multipliers are d(ix)/d(gx) = W/2 or (W-1)/2, zero where
@@ -493,6 +558,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     }
     // ---- SLOW items (taps far from the rest of the tile, or a direction whose footprint does not fit): this thread owns the
     // taps, so it adds its contributions straight to global memory (exact float reductions; grad_out from the staged tile)
+    CL_T(4);
     if (slowbits) {
 #pragma unroll
       for (int d = 0; d < NDIRS; ++d) {
@@ -523,6 +589,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CL_REGS_K3));
 #endif
   const int ctid = tid - CL_NPIX;
+  CL_T0();
   // ---- the grad_out tile travels to shared memory (4-byte cp.async: any plane stride) while the taps are computed.
   // Out-of-image pixels of ragged tiles stage the value of the clamped address: their items carry zero weights.
   {
@@ -588,8 +655,11 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     for (int g = G.n_groups - 1; g >= 0; --g)
       if (Q.grad_out[g] && Q.grad_src[g][d]) gsh[d] = Q.gs_sh[g][d];
   }
+  CL_T(16);
   cp_async_wait<0>();
+  CL_T(17);
   __syncthreads();
+  CL_T(18);
   if (CL_DBG & 2) return;  // timing experiment: the pixel role alone
 
 
@@ -604,6 +674,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     for (int u = 0; u < 32; ++u) m = max(m, __float_as_uint(gl[u]) & 0x7fffffffu);
     if (m != 0u) atomicMax(&amax_s[lane], m);
   }
+  CL_T(19);
   float S = 0.f, magic = 0.f;
   bool finite = true, any_nonfinite = false, scaled = false;
 #pragma unroll 1
@@ -618,7 +689,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       const int n4 = ((Cn + 1) * PS + 3) >> 2;
       for (int q = ctid; q < n4; q += CL_NPIX) asm volatile("st.shared.v4.s32 [%0], {%1,%1,%1,%1};" ::"r"(acc_s + 16u * (unsigned)q), "r"(0) : "memory");
     }
+    CL_T(20 + 8 * d);
     cl_bar(2);  // the planes are clear; (first round) the maxima of all eight warps are in
+    CL_T(21 + 8 * d);
     if (!scaled) {  // scale of this lane's channel
       scaled = true;
       if (lane < Cn) {
@@ -655,7 +728,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         cl_red_s32_4(a1, __float_as_int(fmaf(gsv, w.w, magic)));
       }
     }
+    CL_T(22 + 8 * d);
     cl_bar(2);
+    CL_T(23 + 8 * d);
     // flush: two halves of 128 threads, half h takes the planes cf = h, h + 2, ...
     const int half = ctid >> 7, htid = ctid & 127;
     const int nsl = (T.cells + CL_NPIX / 2 - 1) / (CL_NPIX / 2);
@@ -681,6 +756,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         }
       }
     }
+    CL_T(24 + 8 * d);
     const unsigned ps_b = 4u * (unsigned)PS;
     const unsigned ap0 = acc_s + 4u * (unsigned)(CL_ZPAD + htid);
     const int ngrp = ngrp_s;
@@ -703,7 +779,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
         default: cl_flush_planes<6>(gsp, 2 * gsc, np, si, ap, 2 * ps_b, goff, cmb, last_on); break;
       }
     }
+    CL_T(25 + 8 * d);
     cl_bar(2);  // the planes are reused by the next direction; sinv_s is read by every warp
+    CL_T(26 + 8 * d);
   }
   // the cached SLOW items: exact float reductions, lane = channel
   {
@@ -717,11 +795,16 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       }
     }
   }
+  CL_T(44);
   // every (fast) item of a non-finite channel: exact float atomics, lane = channel
   if (any_nonfinite) {
     for (int u = 0; u < 32; ++u) {
       const int sp = (pw << 5) | u;
+#if CL_PATCH
       const int sj = blockIdx.x * CL_TW + (pw & 3) * 8 + (u & 7), si = blockIdx.y * CL_TH + (pw >> 2) * 4 + (u >> 3);
+#else
+      const int sj = blockIdx.x * CL_TW + u, si = blockIdx.y * CL_TH + pw;
+#endif
       for (int d = 0; d < NDIRS; ++d)
         if (oo[d * CL_NPIX + sp].x != 0u) cl_exact_item<NDIRS>(P, Q, chan, gos, Cn, n, t, si, sj, sp, d, !finite);
     }

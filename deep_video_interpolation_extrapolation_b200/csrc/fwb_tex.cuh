@@ -61,6 +61,50 @@ constexpr int TXF_THREADS = 256;
 constexpr int TXF_CB = 4;  // channels per batch of texture fetches
 constexpr int TXF_TW = 32, TXF_TH = 8;  // CTA tile: 4 x 2 warp patches of 8 x 4 pixels
 
+// One batch of NB channels of the forward: every texture fetch of the batch is issued before the first result is used; the
+// output pointer and the texture rows advance by one plane per channel (no per-channel index arithmetic).
+template <int NDIRS>
+struct TxfLoop {
+  unsigned long long tx[NDIRS];
+  float row[NDIRS];  // texture row of the quad's lower row in the current channel (integers below 2^24: exact)
+  float* out;
+  int out_sc;
+};
+template <int NDIRS, int NB, bool MASKED>
+__device__ __forceinline__ void txf_batch(TxfLoop<NDIRS>& L, const float (&fx1)[NDIRS], float fH, const float (&w)[NDIRS][4],
+                                          const float (&bl)[NDIRS], const unsigned (&m)[NDIRS][4], bool in) {
+  float4 q[NB][NDIRS];
+#pragma unroll
+  for (int u = 0; u < NB; ++u)
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)L.tx[d], fx1[d], __fmaf_rn((float)u, fH, L.row[d]), 0);
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) L.row[d] = __fmaf_rn((float)NB, fH, L.row[d]);
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    float r = 0.0f;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
+      float a = q[u][d].w, b = q[u][d].z, cc = q[u][d].x, dd = q[u][d].y;
+      if (MASKED) {
+        a = __uint_as_float(__float_as_uint(a) & m[d][0]);
+        b = __uint_as_float(__float_as_uint(b) & m[d][1]);
+        cc = __uint_as_float(__float_as_uint(cc) & m[d][2]);
+        dd = __uint_as_float(__float_as_uint(dd) & m[d][3]);
+      }
+      float s = __fmul_rn(a, w[d][0]);
+      s = __fmaf_rn(b, w[d][1], s);
+      s = __fmaf_rn(cc, w[d][2], s);
+      s = __fmaf_rn(dd, w[d][3], s);
+      s = __fmul_rn(s, bl[d]);
+      r = (d == 0) ? s : __fadd_rn(r, s);
+    }
+    if (in) __stcs(L.out, r);
+    L.out += L.out_sc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel 1 on the texture path: one thread per output pixel, all directions, all channel groups.
 // Arithmetic identical to fwd_generic_pixel (nw, ne, sw, se; * blend; sum of the directions).
@@ -102,7 +146,7 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
 #endif
   float w[NDIRS][4], bl[NDIRS], fx1[NDIRS], fy1[NDIRS];
   unsigned v[NDIRS];
-  bool has_bl[NDIRS];
+  bool part = false;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
     Tap k;
@@ -112,50 +156,53 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
     w[d][2] = __fmul_rn(k.ux, k.ty);
     w[d][3] = __fmul_rn(k.tx, k.ty);
     v[d] = k.valid;
-    bl[d] = k.blend;
-    has_bl[d] = P.dir[d].blend != nullptr;
+    bl[d] = k.blend;  // 1.0 without a blend weight: s * 1.0 == s bit for bit
+    part |= k.valid != 15u;
     // a pixel without any valid tap fetches texel (0, 0) of the slab (any address will do, the values are masked)
     fx1[d] = k.valid ? (float)(k.x0 + 1) : 0.0f;
     fy1[d] = k.valid ? (float)(k.y0 + 1) : 0.0f;
   }
+  // a warp whose 32 x NDIRS quads lie inside the image (the common case) runs the channel loop without the validity selects
+  const bool masked = __any_sync(0xffffffffu, part);
+  const float fH = (float)G.H;
   for (int g = 0; g < G.n_groups; ++g) {
     const GroupP& R = P.grp[g];
-    unsigned long long tx[NDIRS];
-    float row[NDIRS];
+    TxfLoop<NDIRS> L;
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {
       const TexSrc& S = X.s[g][d];
       const int blk = n / S.nb;
-      tx[d] = S.tex[blk];
-      row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+      L.tx[d] = S.tex[blk];
+      L.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
     }
-    float* out = R.out + n * R.out_sn + t * R.out_st + (long long)i * R.out_sh + j;
-    const float fH = (float)G.H;
-    // channels in batches of TXF_CB: all texture fetches of a batch are issued before the first result is used
-    for (int c0 = 0; c0 < R.C; c0 += TXF_CB) {
-      float4 q[TXF_CB][NDIRS];
+    L.out = R.out + n * R.out_sn + t * R.out_st + (long long)min(i, G.H - 1) * R.out_sh + min(j, G.W - 1);
+    L.out_sc = R.out_sc;
+    const int C = R.C;
+    if (!masked) {
+      unsigned m[NDIRS][4];
+      int c = 0;
+#pragma unroll 1
+      for (; c + TXF_CB <= C; c += TXF_CB) txf_batch<NDIRS, TXF_CB, false>(L, fx1, fH, w, bl, m, in);
+      switch (C - c) {
+        case 1: txf_batch<NDIRS, 1, false>(L, fx1, fH, w, bl, m, in); break;
+        case 2: txf_batch<NDIRS, 2, false>(L, fx1, fH, w, bl, m, in); break;
+        case 3: txf_batch<NDIRS, 3, false>(L, fx1, fH, w, bl, m, in); break;
+        default: break;
+      }
+    } else {
+      unsigned m[NDIRS][4];  // all-ones / zero per tap: a tap outside the image counts as the value 0 (AND on the fetched bits)
 #pragma unroll
-      for (int u = 0; u < TXF_CB; ++u)
+      for (int d = 0; d < NDIRS; ++d)
 #pragma unroll
-        for (int d = 0; d < NDIRS; ++d)  // rows past the last channel stay inside the slab or clamp: fetched, never used
-          q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)tx[d], fx1[d], row[d] + (float)u * fH, 0);
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) row[d] += (float)TXF_CB * fH;  // integers below 2^24: exact
-#pragma unroll
-      for (int u = 0; u < TXF_CB; ++u) {
-        float r = 0.0f;
-#pragma unroll
-        for (int d = 0; d < NDIRS; ++d) {
-          const float a = (v[d] & 1u) ? q[u][d].w : 0.0f, b = (v[d] & 2u) ? q[u][d].z : 0.0f;
-          const float cc = (v[d] & 4u) ? q[u][d].x : 0.0f, dd = (v[d] & 8u) ? q[u][d].y : 0.0f;
-          float s = __fmul_rn(a, w[d][0]);
-          s = __fmaf_rn(b, w[d][1], s);
-          s = __fmaf_rn(cc, w[d][2], s);
-          s = __fmaf_rn(dd, w[d][3], s);
-          if (has_bl[d]) s = __fmul_rn(s, bl[d]);
-          r = (d == 0) ? s : __fadd_rn(r, s);
-        }
-        if (in && c0 + u < R.C) __stcs(out + (long long)(c0 + u) * R.out_sc, r);
+        for (int q = 0; q < 4; ++q) m[d][q] = (v[d] >> q) & 1u ? 0xffffffffu : 0u;
+      int c = 0;
+#pragma unroll 1
+      for (; c + TXF_CB <= C; c += TXF_CB) txf_batch<NDIRS, TXF_CB, true>(L, fx1, fH, w, bl, m, in);
+      switch (C - c) {
+        case 1: txf_batch<NDIRS, 1, true>(L, fx1, fH, w, bl, m, in); break;
+        case 2: txf_batch<NDIRS, 2, true>(L, fx1, fH, w, bl, m, in); break;
+        case 3: txf_batch<NDIRS, 3, true>(L, fx1, fH, w, bl, m, in); break;
+        default: break;
       }
     }
   }
@@ -173,6 +220,47 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
     }
   }
 #endif
+}
+
+// One batch of NB channels of kernel 2: all texture fetches and grad_out loads of the batch are issued before the first use.
+template <int NDIRS>
+struct TxbLoop {
+  unsigned long long th[NDIRS];
+  float row[NDIRS];
+  const float* go;  // grad_out of this pixel in the current channel
+  int go_sc;
+};
+template <int NDIRS, int NB, bool MASKED>
+__device__ __forceinline__ void txb_batch(TxbLoop<NDIRS>& L, const float (&fx1)[NDIRS], float fH, float (&A)[NDIRS][4],
+                                          const unsigned (&m)[NDIRS][4]) {
+  float4 q[NB][NDIRS];
+  float gv[NB];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    gv[u] = __ldcs(L.go);
+    L.go += L.go_sc;
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)L.th[d], fx1[d], __fmaf_rn((float)u, fH, L.row[d]), 0);
+  }
+#pragma unroll
+  for (int d = 0; d < NDIRS; ++d) L.row[d] = __fmaf_rn((float)NB, fH, L.row[d]);
+#pragma unroll
+  for (int u = 0; u < NB; ++u)
+#pragma unroll
+    for (int d = 0; d < NDIRS; ++d) {
+      // TLD4 component order: w = (x0,y0) z = (x0+1,y0) x = (x0,y0+1) y = (x0+1,y0+1)
+      float a = q[u][d].w, b = q[u][d].z, cc = q[u][d].x, dd = q[u][d].y;
+      if (MASKED) {
+        a = __uint_as_float(__float_as_uint(a) & m[d][0]);
+        b = __uint_as_float(__float_as_uint(b) & m[d][1]);
+        cc = __uint_as_float(__float_as_uint(cc) & m[d][2]);
+        dd = __uint_as_float(__float_as_uint(dd) & m[d][3]);
+      }
+      A[d][0] = fmaf(gv[u], a, A[d][0]);
+      A[d][1] = fmaf(gv[u], b, A[d][1]);
+      A[d][2] = fmaf(gv[u], cc, A[d][2]);
+      A[d][3] = fmaf(gv[u], dd, A[d][3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,61 +289,61 @@ __global__ void __launch_bounds__(TXF_THREADS, 3) bwd_flow_tex_kernel(const __gr
   const int ic = min(i, G.H - 1), jc = min(j, G.W - 1);  // ragged tiles: clamped address, stores masked
   // only what the channel loop needs stays in registers; the gradient multipliers, the raw flow and the gate are recomputed for
   // the final store (once per pixel)
-  float tx[NDIRS], ty[NDIRS], ux[NDIRS], uy[NDIRS], bl[NDIRS];
-  unsigned vld[NDIRS];
-  float gix[NDIRS], giy[NDIRS], gbl[NDIRS], fx1[NDIRS], fy1[NDIRS];
-  bool has_bl[NDIRS];
+  // Only the four sums  A_k = sum_c grad_out_c * tap_k,c  per direction are accumulated in the channel loop (one TLD4 and four
+  // FFMA per channel and direction); the bilinear weights do not depend on the channel and are applied once at the end:
+  //   gix = bl [ty (D - C) + uy (B - A)],  giy = bl [tx (D - B) + ux (C - A)],  gblend = uy (ux A + tx B) + ty (ux C + tx D)
+  // (ATen grid_sampler_2d_backward with the common factors pulled out; taps outside the image count as zero).  The taps are
+  // recomputed for the final store, so nothing but the fetch coordinates and the sums lives across the loop.
+  float fx1[NDIRS], fy1[NDIRS], A[NDIRS][4];
+  unsigned m[NDIRS][4];
+  bool part = false;
 #pragma unroll
   for (int d = 0; d < NDIRS; ++d) {
     Tap k;
     compute_tap(G, P.dir[d], n, t, ic, jc, k);
-    tx[d] = k.tx, ty[d] = k.ty, ux[d] = k.ux, uy[d] = k.uy, bl[d] = k.blend, vld[d] = k.valid;
-    gix[d] = giy[d] = gbl[d] = 0.0f;
-    has_bl[d] = P.dir[d].blend != nullptr;
     fx1[d] = k.valid ? (float)(k.x0 + 1) : 0.0f;
     fy1[d] = k.valid ? (float)(k.y0 + 1) : 0.0f;
+    part |= k.valid != 15u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      m[d][q] = (k.valid >> q) & 1u ? 0xffffffffu : 0u;
+      A[d][q] = 0.0f;
+    }
   }
+  const bool masked = __any_sync(0xffffffffu, part);
   const float fH = (float)G.H;
   for (int g = 0; g < G.n_groups; ++g) {
     const GroupP& R = P.grp[g];
     if (!Q.grad_out[g]) continue;
-    const float* go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
-    unsigned long long th[NDIRS];
-    float row[NDIRS];
+    TxbLoop<NDIRS> L;
+    L.go = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ic * Q.go_sh[g] + jc;
+    L.go_sc = Q.go_sc[g];
 #pragma unroll
     for (int d = 0; d < NDIRS; ++d) {
       const TexSrc& S = X.s[g][d];
       const int blk = n / S.nb;
-      th[d] = S.tex[blk];
-      row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
+      L.th[d] = S.tex[blk];
+      L.row[d] = (float)((n - blk * S.nb) * S.rows_n + t * S.rows_t) + fy1[d];
     }
-    for (int c0 = 0; c0 < R.C; c0 += TXF_CB) {
-      float4 q[TXF_CB][NDIRS];
-      float gv[TXF_CB];
-#pragma unroll
-      for (int u = 0; u < TXF_CB; ++u) {
-        gv[u] = (c0 + u < R.C) ? __ldcs(go + (long long)(c0 + u) * Q.go_sc[g]) : 0.0f;  // a channel past the end contributes 0
-#pragma unroll
-        for (int d = 0; d < NDIRS; ++d) q[u][d] = tex2Dgather<float4>((cudaTextureObject_t)th[d], fx1[d], row[d] + (float)u * fH, 0);
+    const int C = R.C;
+    int c = 0;
+    if (!masked) {
+#pragma unroll 1
+      for (; c + TXF_CB <= C; c += TXF_CB) txb_batch<NDIRS, TXF_CB, false>(L, fx1, fH, A, m);
+      switch (C - c) {
+        case 1: txb_batch<NDIRS, 1, false>(L, fx1, fH, A, m); break;
+        case 2: txb_batch<NDIRS, 2, false>(L, fx1, fH, A, m); break;
+        case 3: txb_batch<NDIRS, 3, false>(L, fx1, fH, A, m); break;
+        default: break;
       }
-#pragma unroll
-      for (int d = 0; d < NDIRS; ++d) row[d] += (float)TXF_CB * fH;
-#pragma unroll
-      for (int u = 0; u < TXF_CB; ++u) {
-#pragma unroll
-        for (int d = 0; d < NDIRS; ++d) {
-          const unsigned v = (c0 + u < R.C) ? vld[d] : 0u;  // (the fetched texels of a channel past the end are not finite-safe)
-          const float a = (v & 1u) ? q[u][d].w : 0.0f, b = (v & 2u) ? q[u][d].z : 0.0f;
-          const float cc = (v & 4u) ? q[u][d].x : 0.0f, dd = (v & 8u) ? q[u][d].y : 0.0f;
-          float gw = gv[u];
-          if (has_bl[d]) {
-            const float top = fmaf(b, tx[d], a * ux[d]), bot = fmaf(dd, tx[d], cc * ux[d]);
-            gbl[d] = fmaf(gv[u], fmaf(bot, ty[d], top * uy[d]), gbl[d]);
-            gw = gv[u] * bl[d];
-          }
-          gix[d] = fmaf(gw, fmaf(ty[d], dd - cc, uy[d] * (b - a)), gix[d]);
-          giy[d] = fmaf(gw, fmaf(tx[d], dd - b, ux[d] * (cc - a)), giy[d]);
-        }
+    } else {
+#pragma unroll 1
+      for (; c + TXF_CB <= C; c += TXF_CB) txb_batch<NDIRS, TXF_CB, true>(L, fx1, fH, A, m);
+      switch (C - c) {
+        case 1: txb_batch<NDIRS, 1, true>(L, fx1, fH, A, m); break;
+        case 2: txb_batch<NDIRS, 2, true>(L, fx1, fH, A, m); break;
+        case 3: txb_batch<NDIRS, 3, true>(L, fx1, fH, A, m); break;
+        default: break;
       }
     }
   }
@@ -264,7 +352,16 @@ __global__ void __launch_bounds__(TXF_THREADS, 3) bwd_flow_tex_kernel(const __gr
     for (int d = 0; d < NDIRS; ++d) {
       Tap k;
       compute_tap(G, P.dir[d], n, t, i, j, k);
-      bwdflow_store(P, Q, d, n, t, i, j, k, gix[d], giy[d], gbl[d]);
+      const float a = A[d][0], b = A[d][1], cc = A[d][2], dd = A[d][3];
+      float gbl = 0.0f, sc = 1.0f;
+      if (P.dir[d].blend != nullptr) {
+        const float top = fmaf(b, k.tx, a * k.ux), bot = fmaf(dd, k.tx, cc * k.ux);
+        gbl = fmaf(bot, k.ty, top * k.uy);
+        sc = k.blend;
+      }
+      const float gix = sc * fmaf(k.ty, dd - cc, k.uy * (b - a));
+      const float giy = sc * fmaf(k.tx, dd - b, k.ux * (cc - a));
+      bwdflow_store(P, Q, d, n, t, i, j, k, gix, giy, gbl);
     }
   }
 }
