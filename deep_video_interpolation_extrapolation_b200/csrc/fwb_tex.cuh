@@ -58,6 +58,14 @@ constexpr int TXF_THREADS = 256;
 #ifndef TXF_ZERO_FIRST
 #define TXF_ZERO_FIRST 1  // zero-fill side job before (1) or after (0) the channel loop
 #endif
+#ifndef TXF_ZSTREAM
+#define TXF_ZSTREAM 1  // zero-fill stores with the evict-first hint (st.global.cs): the zeros are not read again before the backward
+#endif
+#if TXF_ZSTREAM
+#define TXF_ZST(p, v) __stcs(p, v)
+#else
+#define TXF_ZST(p, v) (*(p) = (v))
+#endif
 constexpr int TXF_CB = 4;  // channels per batch of texture fetches
 constexpr int TXF_TW = 32, TXF_TH = 8;  // CTA tile: 4 x 2 warp patches of 8 x 4 pixels
 
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
           if (!zp || (t != 0 && Z.st[g][d] == 0)) continue;  // a source shared by all T frames is cleared by the t == 0 tiles
           zp += n * Z.sn[g][d] + t * Z.st[g][d] + (long long)zi * Z.sh[d] + zj;
           const long long sc = Z.sc[g][d];
-          for (int c = threadIdx.x >> 6; c < C; c += TXF_THREADS / 64) *reinterpret_cast<float4*>(zp + c * sc) = z4;
+          for (int c = threadIdx.x >> 6; c < C; c += TXF_THREADS / 64) TXF_ZST(reinterpret_cast<float4*>(zp + c * sc), z4);
         }
       }
     }
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(TXF_THREADS) fwd_tex_kernel(const __grid_const
         int g, c;
         chan_lookup(P, cf, g, c);
         float* zp = zero_plane(Z, G, g, d, n, t, c);
-        if (zp) *reinterpret_cast<float4*>(zp + (long long)zi * Z.sh[d] + zj) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zp) TXF_ZST(reinterpret_cast<float4*>(zp + (long long)zi * Z.sh[d] + zj), make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }

@@ -15,11 +15,13 @@ hdr = rows[0]
 for r in rows[2:]:
     print('==', r[hdr.index('Kernel Name')])
     for i, h in enumerate(hdr):
-        if h in WANT or 'issue_stalled' in h and h.endswith('per_issue_active.ratio') and 'not_issued' not in h:
+        if h in WANT or (h.startswith('l1tex__') and ('pct_of_peak_sustained_elapsed' in h or 'pct_of_peak_sustained_active' in h)) or 'issue_stalled' in h and h.endswith('per_issue_active.ratio') and 'not_issued' not in h:
             try:
                 v = float(r[i])
             except ValueError:
                 continue
             if 'issue_stalled' in h and v < 0.3:
+                continue
+            if h.startswith('l1tex__') and h not in WANT and (v < 5.0 or '.max.' in h or '.min.' in h or ('.sum.' in h and h.replace('.sum.', '.avg.') in hdr)):
                 continue
             print(f'  {h:90s} {r[i]} {rows[1][i]}')
