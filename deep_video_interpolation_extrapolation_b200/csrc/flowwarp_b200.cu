@@ -1023,10 +1023,14 @@ int32_t fwb_warp_blend_backward_flow(const fwb_problem* p, const fwb_grads* g, v
               if (Q.grad_src[gi][d] && ((long long)Q.gs_sc[gi][d] * (p->grp[gi].C + 1) + (long long)(p->H + 1) * Q.gs_sh[gi][d]) >= 2147483647LL) cl_fits = false;
           if (cl_fits) {
             const dim3 gc((p->W + CL_TW - 1) / CL_TW, (p->H + CL_TH - 1) / CL_TH, p->N * p->T);
+            int go16 = !(p->W & 3);  // 16-byte staging of the grad_out tile: every plane row 16-byte aligned
+            for (int gi = 0; gi < p->n_groups; ++gi)
+              if (Q.grad_out[gi] && (((uintptr_t)Q.grad_out[gi] & 15u) || (Q.go_sn[gi] & 3) || (Q.go_st[gi] & 3) || (Q.go_sc[gi] & 3) || (Q.go_sh[gi] & 3)))
+                go16 = 0;
 #define FWB_LAUNCH_CL(D, A, B)                                                \
   do {                                                                        \
     if ((rc = set_smem(bwd_cl_kernel<D, A, B>, dyn))) return rc;              \
-    bwd_cl_kernel<D, A, B><<<gc, CL_THREADS, dyn, s>>>(P, Q, X, acc_words);   \
+    bwd_cl_kernel<D, A, B><<<gc, CL_THREADS, dyn, s>>>(P, Q, X, acc_words, go16); \
   } while (0)
             const int keyc = (p->n_dirs == 2 ? 4 : 0) | (p->align_corners ? 2 : 0) | (p->padding_mode == FWB_PAD_BORDER ? 1 : 0);
             switch (keyc) {

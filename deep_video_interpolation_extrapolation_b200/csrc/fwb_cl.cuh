@@ -32,7 +32,9 @@ constexpr int CL_ROWS = 64;              // source-row window of a direction (CL
 constexpr int CL_ZPAD = 4;               // dummy cells in front of every plane: the target of items without a tap
 constexpr int CL_SLOTS = 6;              // footprint cells per thread of a flush half (128 threads): <= 768 cells per direction
 constexpr int CL_MAXC = 31;              // channels (lanes 0 .. C-1; lane C counts the taps per footprint cell)
-constexpr int CL_GS = CL_NPIX + 1;       // words between the channels of the staged grad_out tile (odd)
+constexpr int CL_GS = CL_NPIX + 4;       // words between the channels of the staged grad_out tile: 16-byte aligned rows whose
+                                         // 4-word groups of 8 consecutive channels cover the 32 banks (LDS.128 by lane = channel:
+                                         // 3 wavefronts for 24 lanes x 4 pixels, the minimum)
 #ifndef CL_CB_N
 #define CL_CB_N 1
 #endif
@@ -319,7 +321,7 @@ __device__ __forceinline__ void cl_scatter_exact(float* gs, int sh, unsigned vld
 
 template <int NDIRS, bool ALIGN, bool BORDER>
 __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_constant__ Params P, const __grid_constant__ GradP Q,
-                                                               const __grid_constant__ TexP X, int acc_words) {
+                                                               const __grid_constant__ TexP X, int acc_words, int go16) {
   extern __shared__ float4 cl_smem4[];
   __shared__ ClTab tab[NDIRS];
   __shared__ __align__(16) ClChan chan[CL_MAXC];
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   __shared__ int nslow_s, nfar_s;
   __shared__ unsigned amax_s[32];
   __shared__ float sinv_s[32];
-  __shared__ float zeros_s[32];
+  __shared__ __align__(16) float zeros_s[32];
   __shared__ unsigned blmax_s;
   __shared__ unsigned gsmask_s[2];  // per direction: channels (bits) that have a grad_src plane
 
@@ -340,7 +342,10 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   const int pw = warp & 7, pp = (pw << 5) | lane;  // the pixel this thread owns
   // a pixel warp is one 32 x 1 row of the tile: coalesced grad_out staging, conflict-free reads of the staged tile in kernel 2,
   // x-consecutive items in the scatter (the texture rate does not depend on the patch shape)
-#if CL_PATCH
+#if CL_PATCH == 2
+  const int j = blockIdx.x * CL_TW + (pw & 1) * 16 + (lane & 15);
+  const int i = blockIdx.y * CL_TH + (pw >> 1) * 2 + (lane >> 4);
+#elif CL_PATCH
   const int j = blockIdx.x * CL_TW + (pw & 3) * 8 + (lane & 7);
   const int i = blockIdx.y * CL_TH + (pw >> 2) * 4 + (lane >> 3);
 #else
@@ -590,9 +595,36 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
 #endif
   const int ctid = tid - CL_NPIX;
   CL_T0();
-  // ---- the grad_out tile travels to shared memory (4-byte cp.async: any plane stride) while the taps are computed.
-  // Out-of-image pixels of ragged tiles stage the value of the clamped address: their items carry zero weights.
-  {
+  // ---- the grad_out tile travels to shared memory while the taps are computed: 16-byte cp.async when the planes allow it (go16:
+  // W % 4 == 0, 16-byte aligned pointers and strides - a thread copies 4 consecutive pixels of a patch row, channels 4 apart),
+  // else 4-byte copies (any plane stride).  Out-of-image pixels of ragged tiles stage the value of a clamped address: their
+  // items carry zero weights.
+  if (go16) {
+    // chunk q = 4 consecutive pixels: patch pw_ (8 x 4 pixels, pp order), row r_ of the patch, half h_ of the row
+    const int q = ctid & 63, cg = ctid >> 6;
+    const int pw_ = q >> 3, r_ = (q >> 1) & 3, h_ = q & 1;
+#if CL_PATCH == 1
+    const int cj = min(blockIdx.x * CL_TW + (pw_ & 3) * 8 + h_ * 4, G.W - 4), ci = min(blockIdx.y * CL_TH + (pw_ >> 2) * 4 + r_, G.H - 1);
+#else
+#error "the 16-byte staging is written for 8 x 4 patches"
+#endif
+    const unsigned gd0 = (unsigned)__cvta_generic_to_shared(gos + (pw_ << 5) + r_ * 8 + h_ * 4);
+    int cf0 = 0;  // flattened index of the group's channel 0
+    for (int g = 0; g < G.n_groups; ++g) {
+      if (!Q.grad_out[g]) continue;
+      const int C = P.grp[g].C;
+      const long long sc = Q.go_sc[g];
+      const float* gp = Q.grad_out[g] + n * Q.go_sn[g] + t * Q.go_st[g] + (long long)ci * Q.go_sh[g] + cj + cg * sc;
+      unsigned gd = gd0 + 4u * CL_GS * (unsigned)(cf0 + cg);
+      for (int c = cg; c < C; c += 4) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gd), "l"(gp) : "memory");
+        gp += 4 * sc;
+        gd += 16u * CL_GS;
+      }
+      cf0 += C;
+    }
+    cp_async_commit();
+  } else {
     unsigned gd = (unsigned)__cvta_generic_to_shared(gos + pp);
     for (int g = 0; g < G.n_groups; ++g) {
       if (!Q.grad_out[g]) continue;
@@ -670,8 +702,12 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   const float* gl = gos + (lane < Cn ? lane : 0) * CL_GS + (pw << 5);
   if (lane < Cn) {  // max |grad_out| of this lane's channel over the warp's 32 pixels; NaN wins (integer compare of the magnitudes)
     unsigned m = 0u;
-#pragma unroll 8
-    for (int u = 0; u < 32; ++u) m = max(m, __float_as_uint(gl[u]) & 0x7fffffffu);
+#pragma unroll
+    for (int u = 0; u < 32; u += 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gl + u);
+      m = max(max(m, __float_as_uint(g4.x) & 0x7fffffffu), __float_as_uint(g4.y) & 0x7fffffffu);
+      m = max(max(m, __float_as_uint(g4.z) & 0x7fffffffu), __float_as_uint(g4.w) & 0x7fffffffu);
+    }
     if (m != 0u) atomicMax(&amax_s[lane], m);
   }
   CL_T(19);
@@ -716,16 +752,21 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       const unsigned la = acc_s + 4u * (unsigned)(lane * PS);
       const float4* wd = wq + d * CL_NPIX + (pw << 5);
       const uint2* od = oo + d * CL_NPIX + (pw << 5);
-#pragma unroll 4
-      for (int u = 0; u < 32; ++u) {
-        const float gsv = gl[u] * Sd;
-        const float4 w = wd[u];
-        const uint2 o = od[u];
-        const unsigned a0 = la + o.x, a1 = la + o.y;
-        cl_red_s32(a0, __float_as_int(fmaf(gsv, w.x, magic)));
-        cl_red_s32_4(a0, __float_as_int(fmaf(gsv, w.y, magic)));
-        cl_red_s32(a1, __float_as_int(fmaf(gsv, w.z, magic)));
-        cl_red_s32_4(a1, __float_as_int(fmaf(gsv, w.w, magic)));
+#pragma unroll 1
+      for (int u = 0; u < 32; u += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gl + u);  // grad_out of this lane's channel at 4 items
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float gsv = gv[v] * Sd;
+          const float4 w = wd[u + v];
+          const uint2 o = od[u + v];
+          const unsigned a0 = la + o.x, a1 = la + o.y;
+          cl_red_s32(a0, __float_as_int(fmaf(gsv, w.x, magic)));
+          cl_red_s32_4(a0, __float_as_int(fmaf(gsv, w.y, magic)));
+          cl_red_s32(a1, __float_as_int(fmaf(gsv, w.z, magic)));
+          cl_red_s32_4(a1, __float_as_int(fmaf(gsv, w.w, magic)));
+        }
       }
     }
     CL_T(22 + 8 * d);
@@ -800,7 +841,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   if (any_nonfinite) {
     for (int u = 0; u < 32; ++u) {
       const int sp = (pw << 5) | u;
-#if CL_PATCH
+#if CL_PATCH == 2
+      const int sj = blockIdx.x * CL_TW + (pw & 1) * 16 + (u & 15), si = blockIdx.y * CL_TH + (pw >> 1) * 2 + (u >> 4);
+#elif CL_PATCH
       const int sj = blockIdx.x * CL_TW + (pw & 3) * 8 + (u & 7), si = blockIdx.y * CL_TH + (pw >> 2) * 4 + (u >> 3);
 #else
       const int sj = blockIdx.x * CL_TW + u, si = blockIdx.y * CL_TH + pw;

@@ -1005,3 +1005,31 @@ def test_channel_lane_backward_non_finite_and_partial_gradients(pkg, oracle):
     ok = [c for c in range(C) if c not in (3, 7)]
     assert torch.isfinite(g[0, ok]).all()
     assert relerr(g[:, ok], want[:, ok]) <= BWD_TOL
+
+
+def test_fused_backward_grad_out_views_not_16_byte_aligned(pkg, oracle):
+    """The channel-per-lane backward stages the grad_out tile with 16-byte copies when every plane row is 16-byte aligned and
+    with 4-byte copies otherwise: upstream gradients handed over as column-shifted views of wider buffers (row stride W + 4,
+    first element 4 bytes off) must give the gradients of the dense tensors, ragged last tile row included."""
+    N, H, W = 2, 60, 96
+    f0, f1, ff, fb, mf, mb, gos = _blend_inputs(N, H, W)
+    rg = oracle.backward(list(zip(f0, f1)), [ff, fb], gos, blends=[mf, mb], signs=[-1, 1], padding_mode="border")
+    for shifted in (False, True):
+        t0, t1 = [cu(a, True) for a in f0], [cu(a, True) for a in f1]
+        tff, tfb, tmf, tmb = cu(ff, True), cu(fb, True), cu(mf, True), cu(mb, True)
+        outs = pkg.warp_blend(t0, t1, tff, tfb, tmf, tmb)
+        if shifted:
+            tg = []
+            for g in gos:
+                wide = torch.full(g.shape[:-1] + (W + 4,), float("nan"), device="cuda")
+                wide[..., 1:W + 1] = cu(g)
+                tg.append(wide[..., 1:W + 1])
+                assert tg[-1].data_ptr() % 16 != 0 and tg[-1].stride(-1) == 1
+        else:
+            tg = [cu(g) for g in gos]
+        torch.autograd.backward(outs, tg)
+        for g in range(2):
+            assert relerr(t0[g].grad, rg["grad_srcs"][g][0][:, 0]) <= BWD_TOL, shifted
+            assert relerr(t1[g].grad, rg["grad_srcs"][g][1][:, 0]) <= BWD_TOL, shifted
+        assert relerr(tff.grad, rg["grad_flows"][0][:, :, 0]) <= BWD_TOL, shifted
+        assert relerr(tmb.grad, rg["grad_blends"][1]) <= BWD_TOL, shifted
