@@ -38,6 +38,11 @@ constexpr int CL_GS = CL_NPIX + 4;       // words between the channels of the st
 #ifndef CL_CB_N
 #define CL_CB_N 1
 #endif
+#ifndef CL_COMBINE
+#define CL_COMBINE 0  // 1: pre-add the contributions of consecutive items to common footprint cells before the shared atomics
+                      // (A/B: correct, 0.540 against 0.521 ms on config 2 - the uniform branches and the serial pending state cost
+                      // more than the ~25 % of the ATOMS they save at |grad flow| 0.6)
+#endif
 #ifndef CL_PATCH
 #define CL_PATCH 1  // 1: a pixel warp covers an 8 x 4 patch of the tile; 0: a 32 x 1 row (A/B: no difference, 0.559 vs 0.563 ms)
 #endif
@@ -752,6 +757,15 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
       const unsigned la = acc_s + 4u * (unsigned)(lane * PS);
       const float4* wd = wq + d * CL_NPIX + (pw << 5);
       const uint2* od = oo + d * CL_NPIX + (pw << 5);
+      // Consecutive items of a warp (x-neighbours of a patch row) mostly land on the same or on the next footprint cells: their
+      // contributions to a common cell are added in registers first (raw fixed-point bits: integer adds, exact; the tap counter lane
+      // adds its 1s the same way), so a run of k neighbours costs 2 k + 2 ATOMS instead of 4 k.  The comparisons are on the item's
+      // offsets, i.e. warp-uniform.  PA/PB: pending cell pair of the upper / lower tap row, P[0..3] their pending sums.
+#if CL_COMBINE
+      unsigned PA = 0u, PB = 0u;
+      int P0 = 0, P1 = 0, P2 = 0, P3 = 0;
+      bool pend = false;
+#endif
 #pragma unroll 1
       for (int u = 0; u < 32; u += 4) {
         const float4 g4 = *reinterpret_cast<const float4*>(gl + u);  // grad_out of this lane's channel at 4 items
@@ -762,12 +776,43 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
           const float4 w = wd[u + v];
           const uint2 o = od[u + v];
           const unsigned a0 = la + o.x, a1 = la + o.y;
-          cl_red_s32(a0, __float_as_int(fmaf(gsv, w.x, magic)));
-          cl_red_s32_4(a0, __float_as_int(fmaf(gsv, w.y, magic)));
-          cl_red_s32(a1, __float_as_int(fmaf(gsv, w.z, magic)));
-          cl_red_s32_4(a1, __float_as_int(fmaf(gsv, w.w, magic)));
+          const int p0 = __float_as_int(fmaf(gsv, w.x, magic)), p1 = __float_as_int(fmaf(gsv, w.y, magic));
+          const int p2 = __float_as_int(fmaf(gsv, w.z, magic)), p3 = __float_as_int(fmaf(gsv, w.w, magic));
+#if CL_COMBINE
+          if (pend && a0 == PA + 4u && a1 == PB + 4u) {  // one cell to the right: the left column of the pending pair is complete
+            cl_red_s32(PA, P0);
+            cl_red_s32(PB, P2);
+            P0 = P1 + p0, P2 = P3 + p2, P1 = p1, P3 = p3;
+            PA = a0, PB = a1;
+          } else if (pend && a0 == PA && a1 == PB) {  // the same four cells
+            P0 += p0, P1 += p1, P2 += p2, P3 += p3;
+          } else {
+            if (pend) {
+              cl_red_s32(PA, P0);
+              cl_red_s32_4(PA, P1);
+              cl_red_s32(PB, P2);
+              cl_red_s32_4(PB, P3);
+            }
+            P0 = p0, P1 = p1, P2 = p2, P3 = p3;
+            PA = a0, PB = a1;
+            pend = true;
+          }
+#else
+          cl_red_s32(a0, p0);
+          cl_red_s32_4(a0, p1);
+          cl_red_s32(a1, p2);
+          cl_red_s32_4(a1, p3);
+#endif
         }
       }
+#if CL_COMBINE
+      if (pend) {
+        cl_red_s32(PA, P0);
+        cl_red_s32_4(PA, P1);
+        cl_red_s32(PB, P2);
+        cl_red_s32_4(PB, P3);
+      }
+#endif
     }
     CL_T(22 + 8 * d);
     cl_bar(2);
