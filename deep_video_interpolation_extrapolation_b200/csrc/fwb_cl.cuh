@@ -381,6 +381,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     CL_T0();
     ClTaps<NDIRS> k;
     cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic, jc, inimg, k);
+#ifdef CL_DELAY
+    __nanosleep(CL_DELAY);  // experiment: is the kernel bound by the pixel role's latency chain (time grows with the delay) or by throughput?
+#endif
     CL_T(0);
     unsigned slowbits = 0u;
     {
