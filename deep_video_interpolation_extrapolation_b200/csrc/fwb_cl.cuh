@@ -316,8 +316,13 @@ __device__ __forceinline__ void cl_scatter_exact(float* gs, int sh, unsigned vld
   for (int r = 0; r < 2; ++r) {
     float* p0 = gs + off[2 * r];
     const unsigned vv = (vld >> (2 * r)) & 3u;
-    if (vv == 3u && (reinterpret_cast<uintptr_t>(p0) & 7u) == 0u) {
+    const unsigned a16 = (unsigned)(reinterpret_cast<uintptr_t>(p0) & 15u);
+    if (vv == 3u && (a16 & 7u) == 0u) {
       red_add_v2(p0, w[2 * r] * g, w[2 * r + 1] * g);
+    } else if (vv == 3u && a16 == 4u) {
+      // the pair sits in the middle of a 16-byte quad of its row (rows are 16-byte aligned: host-checked for this kernel): one
+      // 16-byte reduction whose outer lanes add an exact 0 - the L2 reduction rate is per operation, not per byte
+      red_add_v4(p0 - 1, make_float4(0.0f, w[2 * r] * g, w[2 * r + 1] * g, 0.0f));
     } else {
 #pragma unroll
       for (int q = 2 * r; q < 2 * r + 2; ++q)
