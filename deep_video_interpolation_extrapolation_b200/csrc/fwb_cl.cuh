@@ -307,6 +307,7 @@ struct ClSlow {  // a SLOW item with its taps (the first CL_SLOWCAP of a tile; t
   int key;      // pixel << 8 | direction << 4 | validity bits
 };
 constexpr int CL_SLOWCAP = 64;
+constexpr unsigned CL_OWNER_MARK = 4u;  // oo[].y of an item with zero weights (its ATOMS, if any, land in the dummy cells in front of a plane)
 
 // grad_src[tap] += w_tap * g for the 4 taps of one item in one plane (ATen grid_sampler_2d_backward's atomicAdd scatter); the
 // (x0, x0+1) pair of a row goes out as one 8-byte vector reduction when both taps are inside the image and the pair is aligned
@@ -328,6 +329,30 @@ __device__ __forceinline__ void cl_scatter_exact(float* gs, int sh, unsigned vld
       for (int q = 2 * r; q < 2 * r + 2; ++q)
         if (vld & (1u << q)) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gs + off[q]), "f"(w[q] * g) : "memory");
     }
+  }
+}
+
+// one SLOW item scattered by the thread that owns its pixel: grad_src[tap] += w_tap * grad_out for every channel, straight to global
+// memory (exact float reductions; grad_out from the staged tile)
+template <int NDIRS>
+__device__ __forceinline__ void cl_owner_scatter(const Params& P, const GradP& Q, const ClTaps<NDIRS>& k, int d, int n, int t,
+                                                 const float* gos, int pp) {
+  const Geo& G = P.geo;
+  const float b = P.dir[d].blend ? k.bl[d] : 1.0f;
+  const float wl = b * k.ux[d], wr = b * k.tx[d];
+  const float w[4] = {wl * k.uy[d], wr * k.uy[d], wl * k.ty[d], wr * k.ty[d]};
+  const float* gv = gos + pp;
+  for (int g = 0; g < G.n_groups; ++g) {
+    if (!Q.grad_out[g]) continue;
+    const int C = P.grp[g].C;
+    float* gs = Q.grad_src[g][d];
+    if (gs) {
+      const int sh = Q.gs_sh[g][d];
+      gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)k.y0[d] * sh + k.x0[d];
+      const long long gsc = Q.gs_sc[g][d];
+      for (int c = 0; c < C; ++c) cl_scatter_exact(gs + c * gsc, sh, k.vld[d], w, gv[c * CL_GS]);
+    }
+    gv += C * CL_GS;
   }
 }
 
@@ -480,6 +505,9 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
               slowtap[slot] = e;
             } else {
               slowbits |= 1u << d;
+              // with two directions the items of the second one are scattered by the channel-role thread of the same pixel
+              // (that role idles when footprints do not fit, while this one still has kernel 2 to do): marked in the descriptor
+              if (NDIRS == 2 && d == 1) o.y = CL_OWNER_MARK;
             }
           }
           w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -583,24 +611,11 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
 #pragma unroll
       for (int d = 0; d < NDIRS; ++d) {
         if (!((slowbits >> d) & 1u)) continue;
-        const float b = P.dir[d].blend ? k.bl[d] : 1.0f;
-        const float wl = b * k.ux[d], wr = b * k.tx[d];
-        const float w[4] = {wl * k.uy[d], wr * k.uy[d], wl * k.ty[d], wr * k.ty[d]};
-        const float* gv = gos + pp;
-        for (int g = 0; g < G.n_groups; ++g) {
-          if (!Q.grad_out[g]) continue;
-          const int C = P.grp[g].C;
-          float* gs = Q.grad_src[g][d];
-          if (gs) {
-            const int sh = Q.gs_sh[g][d];
-            gs += n * Q.gs_sn[g][d] + t * Q.gs_st[g][d] + (long long)k.y0[d] * sh + k.x0[d];
-            const long long gsc = Q.gs_sc[g][d];
-            for (int c = 0; c < C; ++c) cl_scatter_exact(gs + c * gsc, sh, k.vld[d], w, gv[c * CL_GS]);
-          }
-          gv += C * CL_GS;
-        }
+        if (NDIRS == 2 && d == 1) continue;  // (handed to the channel-role thread of this pixel, see CL_OWNER_MARK)
+        cl_owner_scatter<NDIRS>(P, Q, k, d, n, t, gos, pp);
       }
     }
+    CL_T(5);
     return;
   }
 
@@ -892,6 +907,15 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
     }
   }
   CL_T(44);
+  // the owner-scattered items of the second direction: this thread's pixel is pp as well; taps recomputed (flow / mask reloads hit the L1)
+  if (NDIRS == 2) {
+    const uint2 om = oo[CL_NPIX + pp];
+    if (__any_sync(0xffffffffu, om.x == 0u && om.y == CL_OWNER_MARK)) {
+      ClTaps<NDIRS> k;
+      cl_taps<NDIRS, ALIGN, BORDER>(P, n, t, ic, jc, inimg, k);
+      if (om.x == 0u && om.y == CL_OWNER_MARK) cl_owner_scatter<NDIRS>(P, Q, k, 1, n, t, gos, pp);
+    }
+  }
   // every (fast) item of a non-finite channel: exact float atomics, lane = channel
   if (any_nonfinite) {
     for (int u = 0; u < 32; ++u) {

@@ -21,7 +21,7 @@ for _ in range(reps):
 st.lib.fwb_debug_cl_prof(buf)
 tiles = cfg["N"] * ((cfg["H"] + 7) // 8) * ((cfg["W"] + 31) // 32) * reps
 names = {0: "px taps", 1: "px tables+descriptors", 2: "px wait syncthreads", 3: "px kernel 2 loop", 4: "px epilogue",
-         16: "ch staging issue+chan table", 17: "ch cp.async wait", 18: "ch wait syncthreads", 19: "ch amax",
+         5: "px own SLOW scatter", 16: "ch staging issue+chan table", 17: "ch cp.async wait", 18: "ch wait syncthreads", 19: "ch amax",
          20: "ch d0 clear", 21: "ch d0 bar", 22: "ch d0 scatter", 23: "ch d0 bar", 24: "ch d0 flush setup", 25: "ch d0 flush", 26: "ch d0 bar",
          28: "ch d1 clear", 29: "ch d1 bar", 30: "ch d1 scatter", 31: "ch d1 bar", 32: "ch d1 flush setup", 33: "ch d1 flush", 34: "ch d1 bar",
          44: "ch slow items", 45: "ch initial fill"}
