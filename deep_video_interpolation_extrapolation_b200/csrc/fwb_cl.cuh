@@ -46,7 +46,7 @@ constexpr int CL_GS = CL_NPIX + 4;       // words between the channels of the st
                       // more than the ~25 % of the ATOMS they save at |grad flow| 0.6)
 #endif
 #ifndef CL_PATCH
-#define CL_PATCH 1  // 1: a pixel warp covers an 8 x 4 patch of the tile; 0: a 32 x 1 row (A/B: no difference, 0.559 vs 0.563 ms)
+#define CL_PATCH 2  // the pixels of a warp: 2 = a 16 x 2 patch of the tile (0.515 ms on config 2), 1 = 8 x 4 (0.521), 0 = a 32 x 1 row (0.535)
 #endif
 #ifndef CL_DBG
 #define CL_DBG 0  // 2: the channel role returns after staging grad_out (timing experiment: the pixel role alone)
@@ -632,13 +632,20 @@ __global__ void __launch_bounds__(CL_THREADS, 2) bwd_cl_kernel(const __grid_cons
   if (go16) {
     // chunk q = 4 consecutive pixels: patch pw_ (8 x 4 pixels, pp order), row r_ of the patch, half h_ of the row
     const int q = ctid & 63, cg = ctid >> 6;
-    const int pw_ = q >> 3, r_ = (q >> 1) & 3, h_ = q & 1;
-#if CL_PATCH == 1
+    const int pw_ = q >> 3;
+#if CL_PATCH == 1  // 8 x 4 patches: row r_ of the patch, half h_ of the row
+    const int r_ = (q >> 1) & 3, h_ = q & 1;
     const int cj = min(blockIdx.x * CL_TW + (pw_ & 3) * 8 + h_ * 4, G.W - 4), ci = min(blockIdx.y * CL_TH + (pw_ >> 2) * 4 + r_, G.H - 1);
-#else
-#error "the 16-byte staging is written for 8 x 4 patches"
-#endif
     const unsigned gd0 = (unsigned)__cvta_generic_to_shared(gos + (pw_ << 5) + r_ * 8 + h_ * 4);
+#elif CL_PATCH == 2  // 16 x 2 patches: row r_ of the patch, quarter h_ of the row
+    const int r_ = (q >> 2) & 1, h_ = q & 3;
+    const int cj = min(blockIdx.x * CL_TW + (pw_ & 1) * 16 + h_ * 4, G.W - 4), ci = min(blockIdx.y * CL_TH + (pw_ >> 1) * 2 + r_, G.H - 1);
+    const unsigned gd0 = (unsigned)__cvta_generic_to_shared(gos + (pw_ << 5) + r_ * 16 + h_ * 4);
+#else  // 32 x 1 rows: eighth h_ of the row
+    const int h_ = q & 7;
+    const int cj = min(blockIdx.x * CL_TW + h_ * 4, G.W - 4), ci = min(blockIdx.y * CL_TH + pw_, G.H - 1);
+    const unsigned gd0 = (unsigned)__cvta_generic_to_shared(gos + (pw_ << 5) + h_ * 4);
+#endif
     int cf0 = 0;  // flattened index of the group's channel 0
     for (int g = 0; g < G.n_groups; ++g) {
       if (!Q.grad_out[g]) continue;
