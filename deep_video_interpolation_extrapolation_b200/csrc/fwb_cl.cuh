@@ -13,7 +13,7 @@
 //     warps 8-15  (lane = channel)     grad_out tile -> shared memory, scale vote | scatter (ATOMS.ADD.S32) | flush (RED.F32)
 //
 // so that texture fetches and shared-memory traffic are in flight at the same time.  (Both pass through the one L1TEX data stage
-// of the SM, which is what bounds the kernel: 62.5 % LSU + 18.4 % TEX wavefronts, profiles/r2_ncu_full_summary.txt; making one
+// of the SM, which is what bounds the kernel: 62.8 % LSU + 18.8 % TEX wavefronts, profiles/r2_ncu_full_summary.txt; making one
 // role faster makes the other slower, profiles/r2_cl_timeline.txt.)  A CTA owns a 32x8 tile of output pixels
 // of one (n, t); 2 CTAs per SM.  The two directions are scattered one after the other into the same accumulator planes.
 // Fixed point as in fwb_tile.cuh: scale per channel and tile 2^(20 - exponent(max|grad_out| * max|blend|)),
