@@ -13,4 +13,4 @@ for c in ("c2","c4","c5","ref"):
     except Exception as e:
         print(c, "ERR", e)
 EOP
-tail -3 gpurun_out/r2_mg2_c2.err gpurun_out/r2_mg2_c5.err gpurun_out/r2_mg2_ref.err
+tail -n 3 gpurun_out/r2_mg2_c2.err gpurun_out/r2_mg2_c5.err gpurun_out/r2_mg2_ref.err
